@@ -1,0 +1,808 @@
+// rt_api.cu — the C ABI of include/rt_b200.h: context, scene upload (flatten to device
+// SoA + LBVH build) and the render driver.  The driver is the GPU restatement of
+// Scene::renderScene (src/scene.cpp:10-59): instead of N threads pulling 2000-pixel
+// blocks and recursing per pixel, the frame is cut into batches of framebuffer slots and
+// every batch runs the wavefront loop  trace -> shade -> shadow  once per bounce level.
+// Every level owns a ray queue of `cap` slots and a batch never exceeds cap/2 rays, so the
+// <= 2 children per hit (src/scene.cpp:127,134) can never overflow the next level.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_bvh.h"
+#include "rt_kernels.cuh"
+
+using namespace rt;
+
+namespace {
+
+thread_local std::string g_error = "";
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, "%s: %s", #x, \
+                        cudaGetErrorString(e_));                                               \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+struct TileLayout {
+    int width = 0, height = 0, world = 1, rank = 0;
+    int tiles_x = 0, tiles_y = 0;
+    std::vector<int> ids;            // this rank's tiles, global row-major order
+    void build(int w, int h, int rank_, int world_) {
+        width = w; height = h; world = world_; rank = rank_;
+        tiles_x = (w + RT_TILE_W - 1) / RT_TILE_W;
+        tiles_y = (h + RT_TILE_H - 1) / RT_TILE_H;
+        ids.clear();
+        for (int ty = 0; ty < tiles_y; ty++)
+            for (int tx = 0; tx < tiles_x; tx++)
+                if ((tx + ty) % world == rank) ids.push_back(ty * tiles_x + tx);
+    }
+    static long long count(int w, int h, int rank, int world) {
+        int tx_n = (w + RT_TILE_W - 1) / RT_TILE_W, ty_n = (h + RT_TILE_H - 1) / RT_TILE_H;
+        long long c = 0;
+        for (int ty = 0; ty < ty_n; ty++) {
+            int first = ((rank - ty) % world + world) % world;
+            if (first < tx_n) c += (tx_n - first + world - 1) / world;
+        }
+        return c;
+    }
+};
+
+}  // namespace
+
+struct rt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_scene = false;
+    // scene
+    DScene S;
+    DevBuf<DGeom> geoms;
+    DevBuf<DMat> mats;
+    DevBuf<DLight> slights, alights;
+    DevBuf<double2> face_pts, face_nrm;
+    DevBuf<int> flat, all_prims, bvh_prims;
+    BvhNode* nodes = nullptr;
+    // render state
+    size_t cap = 0;                         // ray-queue capacity per level
+    std::vector<DevBuf<double>> qf;         // per level: 9*cap doubles
+    std::vector<DevBuf<int>> qi;            // per level: 2*cap ints
+    DevBuf<double> hf;                      // 13*(cap/2)
+    DevBuf<int> hi;                         // 3*(cap/2)
+    DevBuf<double> fb;                      // framebuffer, slot order
+    DevBuf<int> tile_ids;
+    DevBuf<int> ids_geom, ids_face;
+    DevBuf<unsigned long long> ctr;
+    DevBuf<unsigned char> staging;          // resolve target for the host-buffer entry points
+    unsigned long long* h_ctr = nullptr;    // pinned
+    TileLayout tiles;
+    rt_stats stats;
+    rt_context() { memset(&S, 0, sizeof(S)); memset(&stats, 0, sizeof(stats)); }
+};
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_error.c_str(); }
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+int rt_create(int device, rt_context** out) {
+    if (!out) return fail(RT_ERR_INVALID, "rt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RT_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return fail(RT_ERR_NO_DEVICE, "CUDA device %d does not exist (%d present)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(RT_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100-class; kernels are built for sm_100a only",
+                    device, prop.name, prop.major, prop.minor);
+    rt_context* ctx = new rt_context();
+    ctx->device = device;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0));
+    CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * CTR_COUNT));
+    CU(ctx->ctr.ensure(CTR_COUNT + 1));
+    const char* capenv = getenv("RT_QUEUE_CAP");
+    ctx->cap = capenv ? (size_t)atoll(capenv) : ((size_t)8 << 20);
+    if (ctx->cap < 2 * RT_TILE_PIXELS) ctx->cap = 2 * RT_TILE_PIXELS;
+    ctx->cap = ctx->cap / (2 * RT_TILE_PIXELS) * (2 * RT_TILE_PIXELS);
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(rt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->nodes) cudaFree(ctx->nodes);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int validate_scene(const rt_scene* s) {
+    if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+    if (s->num_geometries < 0 || s->num_lights < 0 || s->num_materials < 0 || s->num_faces < 0)
+        return fail(RT_ERR_INVALID, "negative count in scene descriptor");
+    if (s->num_faces > PRIM_INDEX_MASK) return fail(RT_ERR_INVALID, "too many faces (%lld)", (long long)s->num_faces);
+    if ((s->num_geometries && !s->geometries) || (s->num_lights && !s->lights) ||
+        (s->num_materials && !s->materials) || (s->num_faces && (!s->face_points || !s->face_normals)))
+        return fail(RT_ERR_INVALID, "NULL array in scene descriptor");
+    for (int i = 0; i < s->num_geometries; i++) {
+        const rt_geometry& g = s->geometries[i];
+        if (g.type != RT_GEOM_SPHERE && g.type != RT_GEOM_TRI && g.type != RT_GEOM_MESH)
+            return fail(RT_ERR_INVALID, "geometry %d: unknown type %d", i, g.type);
+        if (g.material < 0 || g.material >= s->num_materials)
+            return fail(RT_ERR_INVALID, "geometry %d: material index %d out of range", i, g.material);
+        if (g.type != RT_GEOM_SPHERE) {
+            if (g.first_face < 0 || g.num_faces < 0 || g.first_face + g.num_faces > s->num_faces)
+                return fail(RT_ERR_INVALID, "geometry %d: face range out of bounds", i);
+            if (g.type == RT_GEOM_TRI && g.num_faces != 2)
+                return fail(RT_ERR_INVALID, "geometry %d: a `tri` must have exactly 2 faces", i);
+        }
+    }
+    for (int i = 0; i < s->num_lights; i++) {
+        int t = s->lights[i].type;
+        if (t != RT_LIGHT_AMBIENT && t != RT_LIGHT_POINT && t != RT_LIGHT_DIRECTIONAL)
+            return fail(RT_ERR_INVALID, "light %d: unknown type %d", i, t);
+    }
+    return RT_OK;
+}
+
+int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
+    if (!ctx) return fail(RT_ERR_INVALID, "context is NULL");
+    int rc = validate_scene(s);
+    if (rc != RT_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_scene = false;
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, st));
+    int launches = 0;
+
+    // ---- host-side conversion of the small arrays ----
+    const int ng = s->num_geometries;
+    std::vector<DGeom> hg((size_t)ng);
+    std::vector<DMat> hm((size_t)s->num_materials);
+    std::vector<DLight> hsl, hal;
+    for (int i = 0; i < ng; i++) {
+        const rt_geometry& g = s->geometries[i];
+        DGeom& d = hg[(size_t)i];
+        memset(&d, 0, sizeof(d));
+        memcpy(d.inv, g.inv, sizeof(d.inv));
+        memcpy(d.fwd, g.fwd, sizeof(d.fwd));
+        d.det = g.det;
+        memcpy(d.center, g.center, sizeof(d.center));
+        d.radius2 = g.radius2;
+        memcpy(d.bbmin, g.bbmin, sizeof(d.bbmin));
+        memcpy(d.bbmax, g.bbmax, sizeof(d.bbmax));
+        d.type = g.type;
+        d.mat = g.material;
+        d.first_face = (int)g.first_face;
+        d.num_faces = (int)g.num_faces;
+        d.use_bbox = g.use_bbox;
+    }
+    for (int i = 0; i < s->num_materials; i++) {
+        const rt_material& m = s->materials[i];
+        DMat& d = hm[(size_t)i];
+        memset(&d, 0, sizeof(d));
+        memcpy(d.ka, m.ka, sizeof(d.ka));
+        memcpy(d.kd, m.kd, sizeof(d.kd));
+        memcpy(d.ks, m.ks, sizeof(d.ks));
+        memcpy(d.kr, m.kr, sizeof(d.kr));
+        d.sp = m.sp;
+        d.ior = m.ior;
+        d.has_kt = !(m.kt[0] == 0 && m.kt[1] == 0 && m.kt[2] == 0);
+        d.has_kr = !(m.kr[0] == 0 && m.kr[1] == 0 && m.kr[2] == 0);
+    }
+    for (int i = 0; i < s->num_lights; i++) {
+        const rt_light& l = s->lights[i];
+        DLight d;
+        memset(&d, 0, sizeof(d));
+        memcpy(d.v, l.v, sizeof(d.v));
+        memcpy(d.color, l.color, sizeof(d.color));
+        d.falloff = l.falloff;
+        d.type = l.type;
+        (l.type == RT_LIGHT_AMBIENT ? hal : hsl).push_back(d);
+    }
+
+    // ---- primitive codes: reference order, then the flat / BVH split ----
+    std::vector<int> all_codes, simple_codes, face_geom((size_t)s->num_faces, 0), face_local((size_t)s->num_faces, 0);
+    size_t n_mesh_faces = 0;
+    for (int i = 0; i < ng; i++)
+        if (s->geometries[i].type == RT_GEOM_MESH) n_mesh_faces += (size_t)s->geometries[i].num_faces;
+    all_codes.reserve(n_mesh_faces + (size_t)ng);
+    for (int i = 0; i < ng; i++) {
+        const rt_geometry& g = s->geometries[i];
+        if (g.type == RT_GEOM_SPHERE) {
+            all_codes.push_back((PRIM_SPHERE << PRIM_KIND_SHIFT) | i);
+            simple_codes.push_back(all_codes.back());
+        } else {
+            for (int64_t f = 0; f < g.num_faces; f++) {
+                face_geom[(size_t)(g.first_face + f)] = i;
+                face_local[(size_t)(g.first_face + f)] = (int)f;
+            }
+            if (g.type == RT_GEOM_TRI) {
+                all_codes.push_back((PRIM_TRI << PRIM_KIND_SHIFT) | i);
+                simple_codes.push_back(all_codes.back());
+            } else {
+                for (int64_t f = 0; f < g.num_faces; f++)
+                    all_codes.push_back((PRIM_FACE << PRIM_KIND_SHIFT) | (int)(g.first_face + f));
+            }
+        }
+    }
+    // spheres and `tri`s: few -> tested by every ray in reference order; many -> into the
+    // LBVH, except giants (floors) that would bloat its upper levels.
+    std::vector<int> flat_codes, bvh_codes;
+    const size_t kFlatMax = 64, kGiantMax = 16;
+    if (simple_codes.size() <= kFlatMax) {
+        flat_codes = simple_codes;
+    } else {
+        std::vector<double> ext(simple_codes.size(), 0.0);
+        double ulo[3] = {1e300, 1e300, 1e300}, uhi[3] = {-1e300, -1e300, -1e300};
+        for (size_t k = 0; k < simple_codes.size(); k++) {
+            int code = simple_codes[k], gi = code & PRIM_INDEX_MASK;
+            const rt_geometry& g = s->geometries[gi];
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            auto grow = [&](const double* p) {
+                for (int a = 0; a < 3; a++) {
+                    double w = g.fwd[4 * a] * p[0] + g.fwd[4 * a + 1] * p[1] + g.fwd[4 * a + 2] * p[2] + g.fwd[4 * a + 3];
+                    lo[a] = std::fmin(lo[a], w);
+                    hi[a] = std::fmax(hi[a], w);
+                }
+            };
+            if (g.type == RT_GEOM_SPHERE) {
+                for (int c = 0; c < 8; c++) {
+                    double p[3] = {g.center[0] + ((c & 1) ? g.radius : -g.radius),
+                                   g.center[1] + ((c & 2) ? g.radius : -g.radius),
+                                   g.center[2] + ((c & 4) ? g.radius : -g.radius)};
+                    grow(p);
+                }
+            } else {
+                for (int v = 0; v < 6; v++) grow(s->face_points + 9 * g.first_face + 3 * v);
+            }
+            for (int a = 0; a < 3; a++) {
+                ext[k] = std::fmax(ext[k], hi[a] - lo[a]);
+                ulo[a] = std::fmin(ulo[a], lo[a]);
+                uhi[a] = std::fmax(uhi[a], hi[a]);
+            }
+        }
+        double uext = 0;
+        for (int a = 0; a < 3; a++) uext = std::fmax(uext, uhi[a] - ulo[a]);
+        for (size_t k = 0; k < simple_codes.size(); k++) {
+            if (ext[k] > 0.5 * uext && flat_codes.size() < kGiantMax) flat_codes.push_back(simple_codes[k]);
+            else bvh_codes.push_back(simple_codes[k]);
+        }
+    }
+    for (int code : all_codes)
+        if ((code >> PRIM_KIND_SHIFT) == PRIM_FACE) bvh_codes.push_back(code);
+
+    // ---- uploads ----
+    CU(ctx->geoms.ensure((size_t)ng));
+    CU(ctx->mats.ensure(hm.size()));
+    CU(ctx->slights.ensure(hsl.size()));
+    CU(ctx->alights.ensure(hal.size()));
+    CU(ctx->flat.ensure(flat_codes.size()));
+    CU(ctx->all_prims.ensure(all_codes.size()));
+    CU(ctx->bvh_prims.ensure(bvh_codes.size()));
+    CU(ctx->face_pts.ensure((size_t)s->num_faces * RT_FACE_D2));
+    CU(ctx->face_nrm.ensure((size_t)s->num_faces * RT_FACE_D2));
+    if (ng) CU(cudaMemcpyAsync(ctx->geoms.p, hg.data(), sizeof(DGeom) * hg.size(), cudaMemcpyHostToDevice, st));
+    if (!hm.empty()) CU(cudaMemcpyAsync(ctx->mats.p, hm.data(), sizeof(DMat) * hm.size(), cudaMemcpyHostToDevice, st));
+    if (!hsl.empty()) CU(cudaMemcpyAsync(ctx->slights.p, hsl.data(), sizeof(DLight) * hsl.size(), cudaMemcpyHostToDevice, st));
+    if (!hal.empty()) CU(cudaMemcpyAsync(ctx->alights.p, hal.data(), sizeof(DLight) * hal.size(), cudaMemcpyHostToDevice, st));
+    if (!flat_codes.empty()) CU(cudaMemcpyAsync(ctx->flat.p, flat_codes.data(), sizeof(int) * flat_codes.size(), cudaMemcpyHostToDevice, st));
+    if (!all_codes.empty()) CU(cudaMemcpyAsync(ctx->all_prims.p, all_codes.data(), sizeof(int) * all_codes.size(), cudaMemcpyHostToDevice, st));
+    if (!bvh_codes.empty()) CU(cudaMemcpyAsync(ctx->bvh_prims.p, bvh_codes.data(), sizeof(int) * bvh_codes.size(), cudaMemcpyHostToDevice, st));
+    if (s->num_faces) {
+        DevBuf<double> raw_p, raw_n;
+        DevBuf<int> fg, fl;
+        const size_t nf = (size_t)s->num_faces;
+        CU(raw_p.ensure(nf * 9));
+        CU(raw_n.ensure(nf * 9));
+        CU(fg.ensure(nf));
+        CU(fl.ensure(nf));
+        CU(cudaMemcpyAsync(raw_p.p, s->face_points, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(raw_n.p, s->face_normals, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(fg.p, face_geom.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(fl.p, face_local.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
+        k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p.p, raw_n.p, fg.p, fl.p,
+                                                                  ctx->face_pts.p, ctx->face_nrm.p);
+        launches++;
+        CU(cudaStreamSynchronize(st));
+    }
+    CU(cudaStreamSynchronize(st));
+
+    DScene& S = ctx->S;
+    memset(&S, 0, sizeof(S));
+    memcpy(&S.cam, &s->camera, sizeof(DCamera));
+    S.geoms = ctx->geoms.p;
+    S.mats = ctx->mats.p;
+    S.slights = ctx->slights.p;
+    S.alights = ctx->alights.p;
+    S.face_pts = ctx->face_pts.p;
+    S.face_nrm = ctx->face_nrm.p;
+    S.flat = ctx->flat.p;
+    S.all_prims = ctx->all_prims.p;
+    S.num_geoms = ng;
+    S.num_slights = (int)hsl.size();
+    S.num_alights = (int)hal.size();
+    S.num_flat = (int)flat_codes.size();
+    S.num_all = (int)all_codes.size();
+    S.num_bvh_prims = (int)bvh_codes.size();
+    S.single_leaf = bvh_codes.size() == 1 ? bvh_codes[0] : 0;
+    CU(cudaEventRecord(ctx->ev1, st));
+
+    // ---- LBVH ----
+    if (ctx->nodes) { cudaFree(ctx->nodes); ctx->nodes = nullptr; }
+    cudaEvent_t evb;
+    CU(cudaEventCreate(&evb));
+    if (bvh_codes.size() >= 2) {
+        float eye_abs = 0.f;
+        for (int k = 0; k < 3; k++) eye_abs = fmaxf(eye_abs, (float)fabs(s->camera.eye[k]));
+        char err[256] = "";
+        int brc = build_lbvh(S, ctx->bvh_prims.p, (int)bvh_codes.size(), eye_abs, st, &ctx->nodes, &launches, err, sizeof(err));
+        if (brc != RT_OK) { cudaEventDestroy(evb); return fail(brc, "LBVH build: %s", err); }
+    }
+    S.nodes = ctx->nodes;
+    cudaEventRecord(evb, st);
+    CU(cudaStreamSynchronize(st));
+    float ms0 = 0, ms1 = 0;
+    cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ms1, ctx->ev1, evb);
+    cudaEventDestroy(evb);
+    ctx->stats.ms_upload = ms0;
+    ctx->stats.ms_build = ms1;
+    ctx->stats.kernel_launches = (uint64_t)launches;
+    ctx->have_scene = true;
+    return RT_OK;
+}
+
+}  // extern "C"
+
+// ---- render driver --------------------------------------------------------------
+namespace {
+
+struct RenderJob {
+    rt_context* ctx;
+    const rt_params* p;
+    cudaStream_t st;
+    bool brute, count;
+    int* ids_geom;
+    int* ids_face;
+    unsigned long long* maxbits;   // intersection-only
+    uint64_t launches;
+};
+
+RayQ level_queue(rt_context* ctx, int level) {
+    RayQ q;
+    q.f = ctx->qf[(size_t)level].p;
+    q.pixel = ctx->qi[(size_t)level].p;
+    q.meta = ctx->qi[(size_t)level].p + ctx->cap;
+    q.cap = ctx->cap;
+    return q;
+}
+
+int ensure_level(rt_context* ctx, int level) {
+    if ((int)ctx->qf.size() <= level) {
+        ctx->qf.resize((size_t)level + 1);
+        ctx->qi.resize((size_t)level + 1);
+    }
+    CU(ctx->qf[(size_t)level].ensure(9 * ctx->cap));
+    CU(ctx->qi[(size_t)level].ensure(2 * ctx->cap));
+    return RT_OK;
+}
+
+template <bool BRUTE, bool COUNT>
+void launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h) {
+    k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, h, J.ctx->ctr.p,
+                                                                            J.ids_geom, J.ids_face);
+}
+template <bool BRUTE, bool COUNT>
+void launch_shadow(RenderJob& J, int n, HitQ h) {
+    unsigned long long threads = (unsigned long long)n * (unsigned)J.ctx->S.num_slights;
+    if (!threads) return;
+    k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, J.st>>>(J.ctx->S, h, J.ctx->ctr.p,
+                                                                                                 J.ctx->fb.p);
+    J.launches++;
+}
+
+// Process n rays sitting in level `level`'s queue (and, recursively, everything they spawn).
+int process_level(RenderJob& J, int level, size_t n) {
+    rt_context* ctx = J.ctx;
+    const size_t maxchunk = ctx->cap / 2;
+    HitQ h;
+    h.f = ctx->hf.p;
+    h.pixel = ctx->hi.p;
+    h.geom = ctx->hi.p + maxchunk;
+    h.meta = ctx->hi.p + 2 * maxchunk;
+    h.cap = maxchunk;
+    const bool io = J.p->intersection_only != 0;
+    const bool ids_only = J.ids_geom != nullptr;
+    for (size_t off = 0; off < n; off += maxchunk) {
+        const int m = (int)std::min(maxchunk, n - off);
+        RayQ q = level_queue(ctx, level);
+        CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
+        if (J.brute) { if (J.count) launch_trace<true, true>(J, q, off, m, h); else launch_trace<true, false>(J, q, off, m, h); }
+        else { if (J.count) launch_trace<false, true>(J, q, off, m, h); else launch_trace<false, false>(J, q, off, m, h); }
+        J.launches++;
+        if (ids_only) continue;
+        const unsigned blocks = (unsigned)((m + RT_BLOCK - 1) / RT_BLOCK);
+        if (io) {
+            k_shade_io<<<blocks, RT_BLOCK, 0, J.st>>>(h, ctx->ctr.p, ctx->fb.p, J.maxbits);
+            J.launches++;
+            continue;
+        }
+        const bool last_level = level >= J.p->bounce_depth;
+        RayQ next = q;
+        if (!last_level) {
+            int rc = ensure_level(ctx, level + 1);
+            if (rc != RT_OK) return rc;
+            next = level_queue(ctx, level + 1);
+        }
+        k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, ctx->ctr.p, next, ctx->fb.p);
+        J.launches++;
+        if (J.brute) { if (J.count) launch_shadow<true, true>(J, m, h); else launch_shadow<true, false>(J, m, h); }
+        else { if (J.count) launch_shadow<false, true>(J, m, h); else launch_shadow<false, false>(J, m, h); }
+        CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, J.st));
+        CU(cudaStreamSynchronize(J.st));
+        const unsigned long long nhits = ctx->h_ctr[CTR_HITS], nnext = ctx->h_ctr[CTR_NEXT];
+        ctx->stats.rays_shadow += nhits * (unsigned long long)ctx->S.num_slights;
+        ctx->stats.rays_secondary += nnext;
+        if (nnext > 0) {
+            if (last_level) return fail(RT_ERR_CUDA, "internal: rays spawned past the depth limit");
+            int rc = process_level(J, level + 1, (size_t)nnext);
+            if (rc != RT_OK) return rc;
+        }
+    }
+    return RT_OK;
+}
+
+int check_params(rt_context* ctx, const rt_params* p) {
+    if (!ctx) return fail(RT_ERR_INVALID, "context is NULL");
+    if (!p) return fail(RT_ERR_INVALID, "params is NULL");
+    if (!ctx->have_scene) return fail(RT_ERR_NO_SCENE, "rt_scene_upload has not been called");
+    if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "width and height must be positive");
+    if ((long long)p->width * p->height > 2000000000ll) return fail(RT_ERR_INVALID, "frame too large");
+    if (p->bounce_depth < 0 || p->bounce_depth > 255) return fail(RT_ERR_INVALID, "bounce_depth must be in [0,255]");
+    if (p->tile_world < 1 || p->tile_rank < 0 || p->tile_rank >= p->tile_world)
+        return fail(RT_ERR_INVALID, "tile_rank/tile_world out of range");
+    return RT_OK;
+}
+
+// Renders this rank's tiles into ctx->fb (slot order).  ids: also/only record primary hit ids.
+int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_only, rt_progress_fn cb, void* user) {
+    int rc = check_params(ctx, p);
+    if (rc != RT_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    TileLayout& T = ctx->tiles;
+    if (T.width != p->width || T.height != p->height || T.rank != p->tile_rank || T.world != p->tile_world ||
+        ctx->tile_ids.n != T.ids.size() || T.ids.empty()) {
+        T.build(p->width, p->height, p->tile_rank, p->tile_world);
+        CU(ctx->tile_ids.ensure(T.ids.size()));
+        if (!T.ids.empty())
+            CU(cudaMemcpyAsync(ctx->tile_ids.p, T.ids.data(), sizeof(int) * T.ids.size(), cudaMemcpyHostToDevice, st));
+    }
+    const long long nslots = (long long)T.ids.size() * RT_TILE_PIXELS;
+    CU(ctx->fb.ensure((size_t)nslots * 3));
+    const size_t maxchunk = ctx->cap / 2;
+    CU(ctx->hf.ensure(13 * maxchunk));
+    CU(ctx->hi.ensure(3 * maxchunk));
+    rc = ensure_level(ctx, 0);
+    if (rc != RT_OK) return rc;
+
+    RenderJob J;
+    J.ctx = ctx; J.p = p; J.st = st;
+    J.brute = (p->flags & RT_FLAG_BRUTE_FORCE) != 0;
+    J.count = (p->flags & RT_FLAG_COUNT_WORK) != 0;
+    J.ids_geom = nullptr; J.ids_face = nullptr;
+    J.maxbits = ctx->ctr.p + CTR_COUNT;
+    J.launches = 0;
+    if (ids_only) {
+        CU(ctx->ids_geom.ensure((size_t)nslots));
+        CU(ctx->ids_face.ensure((size_t)nslots));
+        CU(cudaMemsetAsync(ctx->ids_geom.p, 0xff, sizeof(int) * (size_t)nslots, st));
+        CU(cudaMemsetAsync(ctx->ids_face.p, 0xff, sizeof(int) * (size_t)nslots, st));
+        J.ids_geom = ctx->ids_geom.p;
+        J.ids_face = ctx->ids_face.p;
+    }
+    rt_stats& stats = ctx->stats;
+    stats.rays_primary = stats.rays_shadow = stats.rays_secondary = 0;
+    stats.nodes_fetched = stats.tris_tested = stats.spheres_tested = stats.degenerate_rays = 0;
+    CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * (CTR_COUNT + 1), st));
+    if (p->intersection_only) {
+        // std::numeric_limits<double>::min() (src/scene.cpp:51)
+        const unsigned long long dblmin = 0x0010000000000000ull;
+        CU(cudaMemcpyAsync(J.maxbits, &dblmin, sizeof(dblmin), cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemsetAsync(ctx->fb.p, 0, sizeof(double) * (size_t)nslots * 3, st));
+    CU(cudaEventRecord(ctx->ev0, st));
+
+    FrameInfo F;
+    F.width = p->width; F.height = p->height; F.tiles_x = T.tiles_x; F.tiles_y = T.tiles_y; F.tile_ids = ctx->tile_ids.p;
+    const long long total_px = (long long)p->width * p->height;
+    for (long long first = 0; first < nslots; first += (long long)maxchunk) {
+        const int n = (int)std::min<long long>((long long)maxchunk, nslots - first);
+        k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0));
+        J.launches++;
+        rc = process_level(J, 0, (size_t)n);
+        if (rc != RT_OK) return rc;
+        if (cb) {
+            long long done = std::min<long long>((first + n) * (long long)p->tile_world, total_px - 1);
+            cb((int)done, (int)total_px, user);
+        }
+    }
+    if (p->intersection_only && !ids_only && p->tile_world == 1) {
+        // global max normalisation (src/scene.cpp:50-58); with tile_world > 1 the caller
+        // all-reduces the max across ranks first (rt_io_get_max / rt_io_normalize)
+        k_divide<<<(unsigned)(((size_t)nslots * 3 + 255) / 256), 256, 0, st>>>(ctx->fb.p, (size_t)nslots * 3, J.maxbits);
+        J.launches++;
+    }
+    CU(cudaEventRecord(ctx->ev1, st));
+    CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * CTR_COUNT, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    stats.ms_trace = ms;
+    // primary rays == pixels of this rank's tiles that lie inside the frame
+    long long prim = 0;
+    for (int gt : T.ids) {
+        int tx = gt % T.tiles_x, ty = gt / T.tiles_x;
+        int w = std::min(RT_TILE_W, p->width - tx * RT_TILE_W), hgt = std::min(RT_TILE_H, p->height - ty * RT_TILE_H);
+        prim += (long long)w * hgt;
+    }
+    stats.rays_primary = (uint64_t)prim;
+    stats.degenerate_rays = ctx->h_ctr[CTR_DEGENERATE];
+    stats.rays_shadow -= 0;   // degenerate shadow rays are counted separately
+    stats.nodes_fetched = ctx->h_ctr[CTR_NODES];
+    stats.tris_tested = ctx->h_ctr[CTR_TRIS];
+    stats.spheres_tested = ctx->h_ctr[CTR_SPHERES];
+    stats.kernel_launches = J.launches;
+    if (cb) cb((int)total_px, (int)total_px, user);
+    return RT_OK;
+}
+
+template <bool QUANT>
+int resolve_to(rt_context* ctx, const rt_params* p, void* d_out, cudaStream_t st) {
+    const long long nslots = (long long)ctx->tiles.ids.size() * RT_TILE_PIXELS;
+    if (!nslots) return RT_OK;
+    FrameInfo F;
+    F.width = p->width; F.height = p->height; F.tiles_x = ctx->tiles.tiles_x; F.tiles_y = ctx->tiles.tiles_y;
+    F.tile_ids = ctx->tile_ids.p;
+    k_resolve<QUANT><<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(F, ctx->fb.p, nslots, p->tile_world == 1 ? 1 : 0, d_out);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_render_device(rt_context* ctx, const rt_params* p, double* d_out, void* stream) {
+    if (!d_out) return fail(RT_ERR_INVALID, "d_out is NULL");
+    cudaStream_t st = stream ? (cudaStream_t)stream : (ctx ? ctx->stream : nullptr);
+    int rc = render_core(ctx, p, st, false, nullptr, nullptr);
+    if (rc != RT_OK) return rc;
+    rc = resolve_to<false>(ctx, p, d_out, st);
+    if (rc != RT_OK) return rc;
+    CU(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+int rt_render_device_rgb8(rt_context* ctx, const rt_params* p, uint8_t* d_out, void* stream) {
+    if (!d_out) return fail(RT_ERR_INVALID, "d_out is NULL");
+    cudaStream_t st = stream ? (cudaStream_t)stream : (ctx ? ctx->stream : nullptr);
+    int rc = render_core(ctx, p, st, false, nullptr, nullptr);
+    if (rc != RT_OK) return rc;
+    rc = resolve_to<true>(ctx, p, d_out, st);
+    if (rc != RT_OK) return rc;
+    CU(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+static int render_host(rt_context* ctx, const rt_params* p, void* host_out, bool quant, rt_progress_fn cb, void* user) {
+    if (!host_out) return fail(RT_ERR_INVALID, "output buffer is NULL");
+    int rc = check_params(ctx, p);
+    if (rc != RT_OK) return rc;
+    if (p->tile_world != 1) return fail(RT_ERR_INVALID, "host-buffer renders need tile_world == 1 (use rt_render_device*)");
+    rc = render_core(ctx, p, ctx->stream, false, cb, user);
+    if (rc != RT_OK) return rc;
+    const size_t px = (size_t)p->width * p->height;
+    const size_t bytes = px * 3 * (quant ? 1 : sizeof(double));
+    CU(ctx->staging.ensure(bytes));
+    rc = quant ? resolve_to<true>(ctx, p, ctx->staging.p, ctx->stream) : resolve_to<false>(ctx, p, ctx->staging.p, ctx->stream);
+    if (rc != RT_OK) return rc;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    cudaEventRecord(a, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(host_out, ctx->staging.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaEventRecord(b, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "framebuffer readback: %s", cudaGetErrorString(e));
+    ctx->stats.ms_readback = ms;
+    return RT_OK;
+}
+
+int rt_render(rt_context* ctx, const rt_params* p, double* rgb, rt_progress_fn cb, void* user) {
+    return render_host(ctx, p, rgb, false, cb, user);
+}
+int rt_render_rgb8(rt_context* ctx, const rt_params* p, uint8_t* rgb8, rt_progress_fn cb, void* user) {
+    return render_host(ctx, p, rgb8, true, cb, user);
+}
+
+int64_t rt_tile_count(const rt_params* p) {
+    if (!p || p->tile_world < 1) return 0;
+    return TileLayout::count(p->width, p->height, p->tile_rank, p->tile_world);
+}
+int64_t rt_tile_count_total(const rt_params* p) {
+    if (!p) return 0;
+    return (int64_t)((p->width + RT_TILE_W - 1) / RT_TILE_W) * ((p->height + RT_TILE_H - 1) / RT_TILE_H);
+}
+int64_t rt_tile_count_max(const rt_params* p) {
+    if (!p || p->tile_world < 1) return 0;
+    long long m = 0;
+    for (int r = 0; r < p->tile_world; r++) m = std::max(m, TileLayout::count(p->width, p->height, r, p->tile_world));
+    return m;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int unpack_impl(rt_context* ctx, const rt_params* p, const T* d_packed, T* d_frame, void* stream) {
+    if (!ctx || !p || !d_packed || !d_frame) return fail(RT_ERR_INVALID, "rt_unpack_tiles: NULL argument");
+    if (p->width <= 0 || p->height <= 0 || p->tile_world < 1) return fail(RT_ERR_INVALID, "rt_unpack_tiles: bad params");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const int tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W, tiles_y = (p->height + RT_TILE_H - 1) / RT_TILE_H;
+    const int world = p->tile_world;
+    std::vector<int> starts((size_t)world * (tiles_y + 1), 0);
+    for (int r = 0; r < world; r++) {
+        int acc = 0;
+        for (int ty = 0; ty < tiles_y; ty++) {
+            starts[(size_t)r * (tiles_y + 1) + ty] = acc;
+            int first = ((r - ty) % world + world) % world;
+            if (first < tiles_x) acc += (tiles_x - first + world - 1) / world;
+        }
+        starts[(size_t)r * (tiles_y + 1) + tiles_y] = acc;
+    }
+    DevBuf<int> d_starts;
+    CU(d_starts.ensure(starts.size()));
+    CU(cudaMemcpyAsync(d_starts.p, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice, st));
+    const long long npx = (long long)p->width * p->height;
+    k_unpack<T><<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(p->width, p->height, tiles_x, world, rt_tile_count_max(p),
+                                                            d_starts.p, tiles_y, d_packed, d_frame);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+extern "C" {
+
+int rt_unpack_tiles_rgb8(rt_context* ctx, const rt_params* p, const uint8_t* d_packed, uint8_t* d_frame, void* stream) {
+    return unpack_impl<uint8_t>(ctx, p, d_packed, d_frame, stream);
+}
+int rt_unpack_tiles(rt_context* ctx, const rt_params* p, const double* d_packed, double* d_frame, void* stream) {
+    return unpack_impl<double>(ctx, p, d_packed, d_frame, stream);
+}
+
+int rt_primary_ids(rt_context* ctx, const rt_params* p, int32_t* geom, int32_t* face) {
+    if (!geom || !face) return fail(RT_ERR_INVALID, "rt_primary_ids: NULL output");
+    int rc = check_params(ctx, p);
+    if (rc != RT_OK) return rc;
+    if (p->tile_world != 1) return fail(RT_ERR_INVALID, "rt_primary_ids needs tile_world == 1");
+    rt_stats keep = ctx->stats;
+    rc = render_core(ctx, p, ctx->stream, true, nullptr, nullptr);
+    ctx->stats = keep;
+    if (rc != RT_OK) return rc;
+    // ids are in slot order: bring them back and de-tile on the host (parity path, not timed)
+    const TileLayout& T = ctx->tiles;
+    const size_t nslots = T.ids.size() * RT_TILE_PIXELS;
+    std::vector<int> hg(nslots), hf(nslots);
+    CU(cudaMemcpy(hg.data(), ctx->ids_geom.p, sizeof(int) * nslots, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hf.data(), ctx->ids_face.p, sizeof(int) * nslots, cudaMemcpyDeviceToHost));
+    for (size_t lt = 0; lt < T.ids.size(); lt++) {
+        int gt = T.ids[lt], tx = gt % T.tiles_x, ty = gt / T.tiles_x;
+        for (int j = 0; j < RT_TILE_PIXELS; j++) {
+            int w = j >> 5, l = j & 31;
+            int px = tx * RT_TILE_W + (w & 3) * 8 + (l & 7), py = ty * RT_TILE_H + (w >> 2) * 4 + (l >> 3);
+            if (px >= p->width || py >= p->height) continue;
+            size_t dst = (size_t)py * p->width + px, src = lt * RT_TILE_PIXELS + j;
+            geom[dst] = hg[src];
+            face[dst] = hf[src];
+        }
+    }
+    return RT_OK;
+}
+
+int rt_cast_rays(rt_context* ctx, int64_t n, const double* org, const double* dir, const uint8_t* reverse,
+                 uint32_t flags, int32_t* geom, int32_t* face, double* dist, double* point, double* normal) {
+    if (!ctx) return fail(RT_ERR_INVALID, "context is NULL");
+    if (!ctx->have_scene) return fail(RT_ERR_NO_SCENE, "rt_scene_upload has not been called");
+    if (n < 0 || (n && (!org || !dir))) return fail(RT_ERR_INVALID, "rt_cast_rays: bad arguments");
+    if (n == 0) return RT_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<double> d_org, d_dir, d_dist, d_point, d_normal;
+    DevBuf<unsigned char> d_rev;
+    DevBuf<int> d_geom, d_face;
+    const size_t N = (size_t)n;
+    CU(d_org.ensure(3 * N)); CU(d_dir.ensure(3 * N)); CU(d_dist.ensure(N)); CU(d_point.ensure(3 * N)); CU(d_normal.ensure(3 * N));
+    CU(d_geom.ensure(N)); CU(d_face.ensure(N));
+    CU(cudaMemcpy(d_org.p, org, sizeof(double) * 3 * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_dir.p, dir, sizeof(double) * 3 * N, cudaMemcpyHostToDevice));
+    if (reverse) {
+        CU(d_rev.ensure(N));
+        CU(cudaMemcpy(d_rev.p, reverse, N, cudaMemcpyHostToDevice));
+    }
+    const unsigned blocks = (unsigned)((N + RT_BLOCK - 1) / RT_BLOCK);
+    if (flags & RT_FLAG_BRUTE_FORCE)
+        k_query<true><<<blocks, RT_BLOCK, 0, ctx->stream>>>(ctx->S, n, d_org.p, d_dir.p, reverse ? d_rev.p : nullptr, d_geom.p,
+                                                           d_face.p, d_dist.p, d_point.p, d_normal.p);
+    else
+        k_query<false><<<blocks, RT_BLOCK, 0, ctx->stream>>>(ctx->S, n, d_org.p, d_dir.p, reverse ? d_rev.p : nullptr, d_geom.p,
+                                                            d_face.p, d_dist.p, d_point.p, d_normal.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (geom) CU(cudaMemcpy(geom, d_geom.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    if (face) CU(cudaMemcpy(face, d_face.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    if (dist) CU(cudaMemcpy(dist, d_dist.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    if (point) CU(cudaMemcpy(point, d_point.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost));
+    if (normal) CU(cudaMemcpy(normal, d_normal.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_get_stats(rt_context* ctx, rt_stats* out) {
+    if (!ctx || !out) return fail(RT_ERR_INVALID, "rt_get_stats: NULL argument");
+    *out = ctx->stats;
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,396 @@
+// rt_bvh.cu — GPU LBVH build: primitive bounds -> 30-bit Morton codes -> hand-written
+// LSD radix sort (no CUB) -> Karras hierarchy (pure integer, deterministic) -> bottom-up
+// refit -> 64-byte node pairs.  It replaces the reference's only acceleration structure,
+// one object-space AABB per .obj mesh (Mesh::updateBoundingBox src/geometry.cpp:145-162,
+// hitsBoundingBox src/geometry.cpp:5-29).  The boxes only CULL (FP32, padded outward);
+// every hit decision is still the exact FP64 test in rt_device.cuh.
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+
+#include "rt_bvh.h"
+
+namespace rt {
+
+// ---- float <-> ordered int so atomicMin/atomicMax work on floats -----------------
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ord2f(int i) {
+    int j = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(j);
+#else
+    float f;
+    memcpy(&f, &j, 4);
+    return f;
+#endif
+}
+
+// World-space bounds of one primitive (FP64 math, rounded outward to FP32).
+__global__ void k_prim_bounds(DScene S, const int* __restrict__ codes, int n, float* __restrict__ lo,
+                              float* __restrict__ hi, int* __restrict__ gbounds /*[7]: cmin xyz, cmax xyz, maxabs*/) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int code = codes[i];
+    int kind = code >> PRIM_KIND_SHIFT, idx = code & PRIM_INDEX_MASK;
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    auto grow = [&](d3 p) {
+        mn[0] = fmin(mn[0], p.x); mn[1] = fmin(mn[1], p.y); mn[2] = fmin(mn[2], p.z);
+        mx[0] = fmax(mx[0], p.x); mx[1] = fmax(mx[1], p.y); mx[2] = fmax(mx[2], p.z);
+    };
+    auto face_bounds = [&](int gface, const DGeom* g) {
+        const double2* fp = S.face_pts + (size_t)gface * RT_FACE_D2;
+        double2 q0 = fp[0], q1 = fp[1], q2 = fp[2], q3 = fp[3], q4 = fp[4];
+        d3 p0 = mk3(q0.x, q0.y, q1.x), va = mk3(q1.y, q2.x, q2.y), vb = mk3(q3.x, q3.y, q4.x);
+        grow(xf_point(g->fwd, p0));
+        grow(xf_point(g->fwd, p0 + va));
+        grow(xf_point(g->fwd, p0 + vb));
+    };
+    if (kind == PRIM_SPHERE) {
+        const DGeom* g = S.geoms + idx;
+        d3 c = xf_point(g->fwd, mk3(g->center[0], g->center[1], g->center[2]));
+        double r = sqrt(g->radius2) * (1.0 + 1e-7);
+        double cc[3] = {c.x, c.y, c.z};
+        for (int a = 0; a < 3; a++) {
+            const double* row = g->fwd + 4 * a;
+            double e = r * sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
+            mn[a] = cc[a] - e;
+            mx[a] = cc[a] + e;
+        }
+    } else if (kind == PRIM_TRI) {
+        const DGeom* g = S.geoms + idx;
+        face_bounds(g->first_face, g);
+        face_bounds(g->first_face + 1, g);
+    } else {
+        double2 q4 = S.face_pts[(size_t)idx * RT_FACE_D2 + 4];
+        face_bounds(idx, S.geoms + __double2loint(q4.y));
+    }
+    float maxabs = 0.f;
+    for (int a = 0; a < 3; a++) {
+        float l = __double2float_rd(mn[a]), h = __double2float_ru(mx[a]);
+        lo[3 * (size_t)i + a] = l;
+        hi[3 * (size_t)i + a] = h;
+        float c = 0.5f * l + 0.5f * h;
+        atomicMin(&gbounds[a], f2ord(c));
+        atomicMax(&gbounds[3 + a], f2ord(c));
+        maxabs = fmaxf(maxabs, fmaxf(fabsf(l), fabsf(h)));
+    }
+    atomicMax(&gbounds[6], f2ord(maxabs));
+}
+
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_morton(const float* __restrict__ lo, const float* __restrict__ hi, int n,
+                         const int* __restrict__ gbounds, uint32_t* __restrict__ keys, int* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t q[3];
+    for (int a = 0; a < 3; a++) {
+        float cmin = ord2f(gbounds[a]), cmax = ord2f(gbounds[3 + a]);
+        float c = 0.5f * lo[3 * (size_t)i + a] + 0.5f * hi[3 * (size_t)i + a];
+        float ext = cmax - cmin;
+        float u = ext > 0.f ? (c - cmin) / ext : 0.f;
+        int v = (int)(u * 1024.f);
+        q[a] = (uint32_t)min(max(v, 0), 1023);
+    }
+    keys[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    vals[i] = i;
+}
+
+// ---- LSD radix sort, 8-bit digits, stable ------------------------------------------
+#define SORT_THREADS 256
+#define SORT_WARPS (SORT_THREADS / 32)
+
+__global__ void k_sort_hist(const uint32_t* __restrict__ keys, int n, int chunk, int shift, int nblocks,
+                            int* __restrict__ hist /*[256][nblocks]*/) {
+    __shared__ int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    int begin = blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int i = begin + threadIdx.x; i < end; i += SORT_THREADS) atomicAdd(&sh[(keys[i] >> shift) & 255], 1);
+    __syncthreads();
+    hist[threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of `count` ints (count <= 65536) by ONE block of 1024 threads
+__global__ void k_sort_scan(int* __restrict__ data, int count) {
+    __shared__ int warp_sums[32];
+    const int per = (count + 1023) / 1024;
+    int begin = threadIdx.x * per, end = min(begin + per, count);
+    int sum = 0;
+    for (int i = begin; i < end; i++) sum += data[i];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int ws = warp_sums[lane];
+        int wi = ws;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sums[lane] = wi - ws;
+    }
+    __syncthreads();
+    int run = warp_sums[w] + incl - sum;
+    for (int i = begin; i < end; i++) {
+        int v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+__global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
+                               uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int n, int chunk,
+                               int shift, int nblocks, const int* __restrict__ offsets) {
+    __shared__ int base[256];
+    __shared__ int warp_cnt[SORT_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    base[tid] = offsets[tid * nblocks + blockIdx.x];
+    for (int k = 0; k < SORT_WARPS; k++) warp_cnt[k][tid] = 0;
+    __syncthreads();
+    int begin = blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int tile = begin; tile < end; tile += SORT_THREADS) {
+        int i = tile + tid;
+        bool valid = i < end;
+        uint32_t key = valid ? keys_in[i] : 0u;
+        int val = valid ? vals_in[i] : 0;
+        uint32_t digit = valid ? ((key >> shift) & 255u) : (0x10000u + lane);
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        int rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) warp_cnt[w][digit] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            int off = 0;
+            for (int k = 0; k < w; k++) off += warp_cnt[k][digit];
+            int pos = base[digit] + off + rank;
+            keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+        __syncthreads();
+        int tot = 0;
+        for (int k = 0; k < SORT_WARPS; k++) {
+            tot += warp_cnt[k][tid];
+            warp_cnt[k][tid] = 0;
+        }
+        base[tid] += tot;
+        __syncthreads();
+    }
+}
+
+// ---- Karras 2012 ---------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz(i ^ j);
+    return __clz(a ^ b);
+}
+
+// child encoding inside the build: >= 0 internal node, < 0 leaf ~index (sorted position)
+__global__ void k_karras(const uint32_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                         int* __restrict__ parent_int, int* __restrict__ parent_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int lc, rc;
+    if (lo == gamma) { lc = ~gamma; parent_leaf[gamma] = i; } else { lc = gamma; parent_int[gamma] = i; }
+    if (hi == gamma + 1) { rc = ~(gamma + 1); parent_leaf[gamma + 1] = i; } else { rc = gamma + 1; parent_int[gamma + 1] = i; }
+    left[i] = lc;
+    right[i] = rc;
+    if (i == 0) parent_int[0] = -1;
+}
+
+__global__ void k_refit(int n, const int* __restrict__ vals, const float* __restrict__ plo,
+                        const float* __restrict__ phi, const int* __restrict__ left, const int* __restrict__ right,
+                        const int* __restrict__ parent_int, const int* __restrict__ parent_leaf,
+                        float* __restrict__ ilo, float* __restrict__ ihi, int* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cur = parent_leaf[i];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1) == 0) return;     // first arrival waits for the sibling
+        __threadfence();
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; a++) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; }
+        int ch[2] = {left[cur], right[cur]};
+        for (int k = 0; k < 2; k++) {
+            const float *bl, *bh;
+            if (ch[k] < 0) {
+                int p = vals[~ch[k]];
+                bl = plo + 3 * (size_t)p; bh = phi + 3 * (size_t)p;
+            } else {
+                bl = ilo + 3 * (size_t)ch[k]; bh = ihi + 3 * (size_t)ch[k];
+            }
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fminf(lo[a], __ldcg(bl + a));
+                hi[a] = fmaxf(hi[a], __ldcg(bh + a));
+            }
+        }
+        for (int a = 0; a < 3; a++) { ilo[3 * (size_t)cur + a] = lo[a]; ihi[3 * (size_t)cur + a] = hi[a]; }
+        __threadfence();
+        cur = parent_int[cur];
+    }
+}
+
+__global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __restrict__ codes,
+                             const float* __restrict__ plo, const float* __restrict__ phi,
+                             const int* __restrict__ left, const int* __restrict__ right,
+                             const float* __restrict__ ilo, const float* __restrict__ ihi,
+                             const int* __restrict__ gbounds, BvhNode* __restrict__ nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    // pad: a few FP32 ulps at the scene's largest coordinate (covers the slab test's rounding)
+    const float pad = 2e-6f * fmaxf(ord2f(gbounds[6]), 1e-30f);
+    float bx[2][6];
+    int ref[2];
+    int ch[2] = {left[i], right[i]};
+    for (int k = 0; k < 2; k++) {
+        const float *bl, *bh;
+        if (ch[k] < 0) {
+            int p = vals[~ch[k]];
+            bl = plo + 3 * (size_t)p; bh = phi + 3 * (size_t)p;
+            ref[k] = ~codes[p];
+        } else {
+            bl = ilo + 3 * (size_t)ch[k]; bh = ihi + 3 * (size_t)ch[k];
+            ref[k] = ch[k];
+        }
+        for (int a = 0; a < 3; a++) {
+            float l = bl[a], h = bh[a];
+            bx[k][a] = l - pad - fabsf(l) * 2e-7f;
+            bx[k][3 + a] = h + pad + fabsf(h) * 2e-7f;
+        }
+    }
+    BvhNode nd;
+    nd.a = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
+    nd.b = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
+    nd.c = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
+    nd.d = make_int4(ref[0], ref[1], 0, 0);
+    nodes[i] = nd;
+}
+
+#define CK(x)                                                                          \
+    do {                                                                               \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            snprintf(err, errlen, "%s failed: %s", #x, cudaGetErrorString(e_));        \
+            goto fail;                                                                 \
+        }                                                                              \
+    } while (0)
+
+int build_lbvh(const DScene& S, const int* d_codes, int n, float extra_abs, cudaStream_t stream,
+               BvhNode** out_nodes, int* launches, char* err, int errlen) {
+    *out_nodes = nullptr;
+    float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
+    int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
+    int *left = nullptr, *right = nullptr, *pint = nullptr, *pleaf = nullptr, *flags = nullptr;
+    uint32_t *keys0 = nullptr, *keys1 = nullptr;
+    BvhNode* nodes = nullptr;
+    const int T = 256;
+    const int nblk = (n + T - 1) / T;
+    int hb[7];
+    {
+        CK(cudaMalloc(&plo, sizeof(float) * 3 * (size_t)n));
+        CK(cudaMalloc(&phi, sizeof(float) * 3 * (size_t)n));
+        CK(cudaMalloc(&gb, sizeof(int) * 8));
+        int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000,
+                       (int)0x80000000, 0};
+        CK(cudaMemcpyAsync(gb, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        k_prim_bounds<<<nblk, T, 0, stream>>>(S, d_codes, n, plo, phi, gb);
+        (*launches)++;
+        CK(cudaMemcpyAsync(hb, gb, sizeof(hb), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        {   // fold the camera eye into the padding scale (positive float: ordered int == bits)
+            float m = ord2f(hb[6]);
+            if (extra_abs > m) m = extra_abs;
+            int enc;
+            memcpy(&enc, &m, 4);
+            CK(cudaMemcpyAsync(gb + 6, &enc, sizeof(int), cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        if (n < 2) {   // nothing to build: the caller tests the single primitive directly
+            cudaFree(plo); cudaFree(phi); cudaFree(gb);
+            return RT_OK;
+        }
+        CK(cudaMalloc(&keys0, sizeof(uint32_t) * (size_t)n));
+        CK(cudaMalloc(&keys1, sizeof(uint32_t) * (size_t)n));
+        CK(cudaMalloc(&vals0, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&vals1, sizeof(int) * (size_t)n));
+        k_morton<<<nblk, T, 0, stream>>>(plo, phi, n, gb, keys0, vals0);
+        (*launches)++;
+        // radix sort: 4 passes x 8 bits
+        int sblocks = (n + 4095) / 4096;
+        if (sblocks > 256) sblocks = 256;
+        if (sblocks < 1) sblocks = 1;
+        int chunk = (n + sblocks - 1) / sblocks;
+        chunk = (chunk + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
+        CK(cudaMalloc(&hist, sizeof(int) * 256 * (size_t)sblocks));
+        uint32_t *kin = keys0, *kout = keys1;
+        int *vin = vals0, *vout = vals1;
+        for (int pass = 0; pass < 4; pass++) {
+            int shift = pass * 8;
+            k_sort_hist<<<sblocks, SORT_THREADS, 0, stream>>>(kin, n, chunk, shift, sblocks, hist);
+            k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * sblocks);
+            k_sort_scatter<<<sblocks, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n, chunk, shift, sblocks, hist);
+            (*launches) += 3;
+            uint32_t* tk = kin; kin = kout; kout = tk;
+            int* tv = vin; vin = vout; vout = tv;
+        }
+        // after 4 passes the sorted data is back in keys0/vals0 (kin/vin)
+        CK(cudaMalloc(&left, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&right, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&pint, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&pleaf, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&flags, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&ilo, sizeof(float) * 3 * (size_t)n));
+        CK(cudaMalloc(&ihi, sizeof(float) * 3 * (size_t)n));
+        CK(cudaMalloc(&nodes, sizeof(BvhNode) * (size_t)(n - 1)));
+        CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
+        k_karras<<<nblk, T, 0, stream>>>(kin, n, left, right, pint, pleaf);
+        k_refit<<<nblk, T, 0, stream>>>(n, vin, plo, phi, left, right, pint, pleaf, ilo, ihi, flags);
+        k_pack_nodes<<<nblk, T, 0, stream>>>(n, vin, d_codes, plo, phi, left, right, ilo, ihi, gb, nodes);
+        (*launches) += 3;
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+    }
+    cudaFree(plo); cudaFree(phi); cudaFree(gb); cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1);
+    cudaFree(hist); cudaFree(left); cudaFree(right); cudaFree(pint); cudaFree(pleaf); cudaFree(flags);
+    cudaFree(ilo); cudaFree(ihi);
+    *out_nodes = nodes;
+    return RT_OK;
+fail:
+    cudaFree(plo); cudaFree(phi); cudaFree(gb); cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1);
+    cudaFree(hist); cudaFree(left); cudaFree(right); cudaFree(pint); cudaFree(pleaf); cudaFree(flags);
+    cudaFree(ilo); cudaFree(ihi); cudaFree(nodes);
+    return RT_ERR_CUDA;
+}
+
+}  // namespace rt

@@ -1,0 +1,412 @@
+// rt_device.cuh — device-side data layout and the exact FP64 arithmetic of the trace loop.
+//
+// Everything that DECIDES a hit (object-space transforms, sphere quadratic, Cramer's rule,
+// shading-normal cull, closest-distance compare) is evaluated in FP64 with exactly the
+// association order of the reference build (g++ -O2, SSE2 Eigen 3.2.2, no FMA), so hit
+// ids and ray counts match the reference bit for bit; this translation unit MUST be
+// compiled with -fmad=false.  Only the LBVH boxes (culling, conservative) are FP32.
+//
+// Reference map:
+//   xf_point/xf_dir      Transform4d * Vector4d           eigen/.../Transform.h:1244-1267
+//   dot4/norm4           Vector4d dot / norm (SSE2 redux)  eigen/.../Redux.h:131-136,299-305
+//   det3                 Matrix3d::determinant            eigen/.../LU/Determinant.h:18-23,61-69
+//   sphere_object        Sphere::calculateIntNormInObjSpace  src/geometry.cpp:47-67
+//   face_object          Mesh::calculateIntNormInObjSpace    src/geometry.cpp:78-123 (loop body)
+//   mesh_bbox            hitsBoundingBox                     src/geometry.cpp:5-29
+//   to_world             Geometry::calculateIntersectionNormal src/geometry.cpp:39-43
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_b200.h"
+
+namespace rt {
+
+struct d3 {
+    double x, y, z;
+};
+
+__device__ __forceinline__ d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ d3 operator-(d3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ d3 operator*(double s, d3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ d3 vdiv(d3 a, double s) { return mk3(a.x / s, a.y / s, a.z / s); }
+
+// two 2-wide packets added lane-wise, then horizontally: (x0+x2)+(x1+x3); w product is +0
+__device__ __forceinline__ double sum4(double a, double b, double c, double d) { return (a + c) + (b + d); }
+__device__ __forceinline__ double dot4(d3 a, d3 b) { return sum4(a.x * b.x, a.y * b.y, a.z * b.z, 0.0); }
+__device__ __forceinline__ double norm4(d3 a) { return sqrt(dot4(a, a)); }
+// Ray constructor: direction / direction.norm()  (true division; src/rtbase.h:23)
+__device__ __forceinline__ d3 ray_normalize(d3 a) { return vdiv(a, norm4(a)); }
+// Vector4d::normalize(): multiply by the reciprocal (Eigen 3.2 operator/=)
+__device__ __forceinline__ d3 inplace_normalize(d3 a) { return (1.0 / norm4(a)) * a; }
+
+// rows 0..2 of a row-major 3x4 affine matrix
+__device__ __forceinline__ d3 xf_point(const double* __restrict__ m, d3 v) {
+    return mk3(((m[0] * v.x + m[1] * v.y) + m[2] * v.z) + m[3] * 1.0,
+               ((m[4] * v.x + m[5] * v.y) + m[6] * v.z) + m[7] * 1.0,
+               ((m[8] * v.x + m[9] * v.y) + m[10] * v.z) + m[11] * 1.0);
+}
+__device__ __forceinline__ d3 xf_dir(const double* __restrict__ m, d3 v) {
+    return mk3(((m[0] * v.x + m[1] * v.y) + m[2] * v.z) + m[3] * 0.0,
+               ((m[4] * v.x + m[5] * v.y) + m[6] * v.z) + m[7] * 0.0,
+               ((m[8] * v.x + m[9] * v.y) + m[10] * v.z) + m[11] * 0.0);
+}
+// inverse.matrix().transpose() * N, w := 0
+__device__ __forceinline__ d3 xf_normal(const double* __restrict__ inv, d3 n) {
+    return mk3(sum4(inv[0] * n.x, inv[4] * n.y, inv[8] * n.z, 0.0),
+               sum4(inv[1] * n.x, inv[5] * n.y, inv[9] * n.z, 0.0),
+               sum4(inv[2] * n.x, inv[6] * n.y, inv[10] * n.z, 0.0));
+}
+
+__device__ __forceinline__ double det3(d3 c0, d3 c1, d3 c2) {
+    double h012 = c0.x * (c1.y * c2.z - c2.y * c1.z);
+    double h102 = c1.x * (c0.y * c2.z - c2.y * c0.z);
+    double h201 = c2.x * (c0.y * c1.z - c1.y * c0.z);
+    return h012 - h102 + h201;
+}
+
+// ---- device scene ------------------------------------------------------------
+struct alignas(16) DGeom {
+    double inv[12];
+    double fwd[12];
+    double det;
+    double center[3];
+    double radius2;
+    double bbmin[3];
+    double bbmax[3];
+    int type;
+    int mat;
+    int first_face;
+    int num_faces;
+    int use_bbox;
+    int pad_[3];
+};
+
+struct alignas(16) DMat {
+    double ka[3], kd[3], ks[3], kr[3];
+    double sp, ior;
+    int has_kt;        // translucencyColor_ != 0  (src/scene.cpp:115)
+    int has_kr;        // reflectiveColor_ != 0    (src/scene.cpp:130)
+    int pad_[2];
+};
+
+struct alignas(16) DLight {
+    double v[3];
+    double color[3];
+    double falloff;
+    int type;
+    int pad_;
+};
+
+struct DCamera {
+    double eye[3], ll[3], lr[3], ul[3], ur[3];
+};
+
+// One face = 5 x double2 = 80 B: p0.xy | p0.z va.x | va.yz | vb.xy | vb.z aux
+// where va = p1 - p0, vb = p2 - p0 (the subtractions src/geometry.cpp:80-81 does per ray)
+// and aux packs (geometry index, face index within the geometry) as two int32.
+// Normals: n0.xy | n0.z n1.x | n1.yz | n2.xy | n2.z pad.
+#define RT_FACE_D2 5
+
+// LBVH node pair, 64 B: both children's FP32 boxes + two child references.
+// ref >= 0: internal node index; ref < 0: leaf, prim code = ~ref.
+struct alignas(16) BvhNode {
+    float4 a;   // L.lo.xyz, L.hi.x
+    float4 b;   // L.hi.yz,  R.lo.xy
+    float4 c;   // R.lo.z,   R.hi.xyz
+    int4 d;     // left ref, right ref, unused, unused
+};
+
+// prim code: kind in the top 2 bits of a 31-bit value
+#define PRIM_KIND_SHIFT 29
+#define PRIM_FACE 0      // index = global face index (mesh face)
+#define PRIM_SPHERE 1    // index = geometry index
+#define PRIM_TRI 2       // index = geometry index (tests faces first_face, first_face+1)
+#define PRIM_INDEX_MASK ((1 << PRIM_KIND_SHIFT) - 1)
+
+struct DScene {
+    DCamera cam;
+    const DGeom* geoms;
+    const DMat* mats;
+    const DLight* slights;     // non-ambient lights, insertion order (each casts a shadow ray)
+    const DLight* alights;     // ambient lights, insertion order
+    const double2* face_pts;
+    const double2* face_nrm;
+    const BvhNode* nodes;      // null when fewer than two primitives are in the BVH
+    const int* flat;           // prim codes tested by every ray, in geometry order
+    const int* all_prims;      // every prim code in geometry/face order (brute force)
+    int num_geoms;
+    int num_slights;
+    int num_alights;
+    int num_flat;
+    int num_all;
+    int num_bvh_prims;
+    int single_leaf;           // BVH with exactly one primitive: its prim code
+    int pad_;
+};
+
+// ---- hit bookkeeping ------------------------------------------------------------
+struct Best {
+    int geom;        // -1: none
+    int face;
+    double dobj;     // object-space distance t*|d'| (mesh) — compared within a geometry
+    double wd;       // world distance |P - o| (src/scene.cpp:153) — compared across geometries
+    d3 P, N;         // world-space point, un-normalised world normal (after det flip)
+};
+
+// object-space ray of the geometry currently being tested (cached across BVH leaves)
+struct ObjRay {
+    int geom;        // -1: nothing cached
+    int box_ok;      // hitsBoundingBox verdict for MESH geometries with use_bbox
+    d3 o, d, nd;     // origin, unit direction, -direction
+    double dn;       // Vector3d norm of d: sqrt(dx^2 + (dy^2 + dz^2))
+};
+
+struct WorkCounters {
+    unsigned long long nodes, tris, spheres;
+};
+
+__device__ __forceinline__ bool mesh_bbox(d3 o, d3 d, const double* __restrict__ bbmin,
+                                          const double* __restrict__ bbmax) {
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int axis = 0; axis < 3; axis++) {
+#pragma unroll
+        for (int bn = 0; bn < 2; bn++) {
+            double mag = dd[axis];
+            if (mag == 0.0) continue;
+            double t = ((bn ? bbmax[axis] : bbmin[axis]) - oo[axis]) / mag;
+            if (t < 0) continue;
+            bool ok = true;
+#pragma unroll
+            for (int a2 = 0; a2 < 3; a2++) {
+                if (a2 == axis) continue;
+                double ip = oo[a2] + t * dd[a2];
+                if (ip < bbmin[a2] || ip > bbmax[a2]) ok = false;
+            }
+            if (ok) return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ void load_objray(const DScene& S, int gi, d3 o, d3 d, ObjRay& R) {
+    const DGeom* g = S.geoms + gi;
+    R.geom = gi;
+    R.o = xf_point(g->inv, o);
+    R.d = ray_normalize(xf_dir(g->inv, d));
+    R.nd = -R.d;
+    R.dn = sqrt(R.d.x * R.d.x + (R.d.y * R.d.y + R.d.z * R.d.z));
+    R.box_ok = 1;
+    if (g->type == RT_GEOM_MESH && g->use_bbox) R.box_ok = mesh_bbox(R.o, R.d, g->bbmin, g->bbmax) ? 1 : 0;
+}
+
+// Offer a candidate (geometry gi, face f) to the running closest hit.  Within one
+// geometry the reference keeps the accepted face of smallest object-space distance, first
+// face on ties (src/geometry.cpp:108-110); across geometries the smallest world distance,
+// first geometry on ties (src/scene.cpp:153-155).
+__device__ __forceinline__ bool beats(const Best& best, int gi, int f, double dobj, double wd) {
+    if (best.geom < 0) return true;
+    if (gi == best.geom) return dobj < best.dobj || (dobj == best.dobj && f < best.face);
+    return wd < best.wd || (wd == best.wd && gi < best.geom);
+}
+
+// World-space completion of an object-space hit (src/geometry.cpp:39-43) + world distance.
+__device__ __forceinline__ void to_world(const DGeom* g, d3 Pobj, d3 Nobj, d3 o, d3& P, d3& N, double& wd) {
+    P = xf_point(g->fwd, Pobj);
+    N = xf_normal(g->inv, Nobj);
+    if (g->det < 0) N = -N;
+    wd = norm4(P - o);
+}
+
+// ANYHIT = true: shadow query — report as soon as an accepted hit has wd <= limit.
+template <bool ANYHIT>
+__device__ __forceinline__ bool test_sphere(const DScene& S, int gi, d3 o, d3 d, bool reverse, double limit,
+                                            Best& best) {
+    const DGeom* g = S.geoms + gi;
+    d3 oo = xf_point(g->inv, o);
+    d3 dd = ray_normalize(xf_dir(g->inv, d));
+    d3 c = mk3(g->center[0], g->center[1], g->center[2]);
+    d3 ocd = oo - c;
+    double a = dot4(dd, dd);
+    double b = 2 * dot4(dd, ocd);
+    double cc = dot4(ocd, ocd) - g->radius2;
+    double disc = b * b - 4 * a * cc;
+    if (disc < 0) return false;
+    double res = reverse ? (-b + sqrt(disc)) / (2 * a) : (-b - sqrt(disc)) / (2 * a);
+    if (res < 0) return false;
+    d3 Pobj = oo + res * dd;
+    d3 Nobj = Pobj - c;
+    d3 P, N;
+    double wd;
+    to_world(g, Pobj, Nobj, o, P, N, wd);
+    if (ANYHIT) return wd <= limit;
+    if (beats(best, gi, 0, 0.0, wd)) {
+        best.geom = gi; best.face = 0; best.dobj = 0.0; best.wd = wd; best.P = P; best.N = N;
+    }
+    return false;
+}
+
+// One face of a TRI/MESH geometry; R must hold the object-space ray of geometry gi.
+template <bool ANYHIT>
+__device__ __forceinline__ bool test_face(const DScene& S, int gi, int gface, int lface, const ObjRay& R, d3 o,
+                                          bool reverse, double limit, Best& best) {
+    const double2* __restrict__ fp = S.face_pts + (size_t)gface * RT_FACE_D2;
+    double2 q0 = __ldg(fp + 0), q1 = __ldg(fp + 1), q2 = __ldg(fp + 2), q3 = __ldg(fp + 3), q4 = __ldg(fp + 4);
+    d3 p0 = mk3(q0.x, q0.y, q1.x), va = mk3(q1.y, q2.x, q2.y), vb = mk3(q3.x, q3.y, q4.x);
+    d3 rhs = R.o - p0;
+    double dlower = det3(va, vb, R.nd);
+    if (dlower == 0) return false;
+    double a = det3(rhs, vb, R.nd) / dlower;
+    if (a < 0 || a > 1) return false;
+    double b = det3(va, rhs, R.nd) / dlower;
+    if (b < 0 || a + b > 1) return false;
+    double t = det3(va, vb, rhs) / dlower;
+    if (t < 0) return false;
+    double dobj = t * R.dn;
+    if (!ANYHIT && best.geom == gi && (dobj > best.dobj || (dobj == best.dobj && lface > best.face))) return false;
+    const double2* __restrict__ fn = S.face_nrm + (size_t)gface * RT_FACE_D2;
+    double2 m0 = __ldg(fn + 0), m1 = __ldg(fn + 1), m2 = __ldg(fn + 2), m3 = __ldg(fn + 3), m4 = __ldg(fn + 4);
+    d3 n0 = mk3(m0.x, m0.y, m1.x), n1 = mk3(m1.y, m2.x, m2.y), n2 = mk3(m3.x, m3.y, m4.x);
+    double w0 = 1.0 - a - b;
+    d3 tn = (w0 * n0 + a * n1) + b * n2;
+    bool front = dot4(tn, R.d) < 0;
+    if ((!front) != reverse) return false;      // (!hitsFront) ^ reverseNormals -> skip
+    d3 Pobj = p0 + (a * va + b * vb);
+    d3 P, N;
+    double wd;
+    to_world(S.geoms + gi, Pobj, tn, o, P, N, wd);
+    if (ANYHIT) return wd <= limit;
+    if (beats(best, gi, lface, dobj, wd)) {
+        best.geom = gi; best.face = lface; best.dobj = dobj; best.wd = wd; best.P = P; best.N = N;
+    }
+    return false;
+}
+
+// Dispatch one prim code.  Returns true only for ANYHIT occlusion.
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ bool test_prim(const DScene& S, int code, d3 o, d3 d, bool reverse, double limit,
+                                          ObjRay& R, Best& best, WorkCounters& wc) {
+    const int kind = code >> PRIM_KIND_SHIFT, idx = code & PRIM_INDEX_MASK;
+    if (kind == PRIM_SPHERE) {
+        if (COUNT) wc.spheres++;
+        return test_sphere<ANYHIT>(S, idx, o, d, reverse, limit, best);
+    }
+    if (kind == PRIM_TRI) {
+        const DGeom* g = S.geoms + idx;
+        if (R.geom != idx) load_objray(S, idx, o, d, R);
+        if (COUNT) wc.tris += 2;
+        if (test_face<ANYHIT>(S, idx, g->first_face, 0, R, o, reverse, limit, best)) return true;
+        return test_face<ANYHIT>(S, idx, g->first_face + 1, 1, R, o, reverse, limit, best);
+    }
+    // mesh face: geometry/local face index ride in the face record's aux slot
+    double2 q4 = __ldg(S.face_pts + (size_t)idx * RT_FACE_D2 + 4);
+    int gi = __double2loint(q4.y), lf = __double2hiint(q4.y);
+    if (R.geom != gi) load_objray(S, gi, o, d, R);
+    if (!R.box_ok) return false;
+    if (COUNT) wc.tris++;
+    return test_face<ANYHIT>(S, gi, idx, lf, R, o, reverse, limit, best);
+}
+
+// ---- FP32 conservative slab test -------------------------------------------------
+struct FRay {
+    float ox, oy, oz;
+    float ix, iy, iz;   // 1/d (clamped away from 0)
+};
+__device__ __forceinline__ FRay make_fray(d3 o, d3 d) {
+    FRay r;
+    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+    float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+    const float tiny = 1e-30f;
+    if (fabsf(dx) < tiny) dx = copysignf(tiny, dx);
+    if (fabsf(dy) < tiny) dy = copysignf(tiny, dy);
+    if (fabsf(dz) < tiny) dz = copysignf(tiny, dz);
+    r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+    return r;
+}
+// Entry distance of the (already padded) box, or +inf when missed.  tmax is widened by a
+// few ulps and tmin compared against a widened limit, so FP32 rounding can only let MORE
+// boxes through, never fewer.
+__device__ __forceinline__ float slab(const FRay& r, float lx, float ly, float lz, float hx, float hy, float hz,
+                                      float tlimit) {
+    float t0x = (lx - r.ox) * r.ix, t1x = (hx - r.ox) * r.ix;
+    float t0y = (ly - r.oy) * r.iy, t1y = (hy - r.oy) * r.iy;
+    float t0z = (lz - r.oz) * r.iz, t1z = (hz - r.oz) * r.iz;
+    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    tmax = tmax + fabsf(tmax) * 5e-7f + 1e-30f;
+    tmin = tmin - fabsf(tmin) * 5e-7f;
+    bool hit = (tmin <= tmax) && (tmax >= 0.f) && (tmin <= tlimit);
+    return hit ? fmaxf(tmin, 0.f) : __int_as_float(0x7f800000);
+}
+
+#define RT_STACK 64
+
+// The closest-hit / any-hit query == Scene::castRay (src/scene.cpp:142-167).
+//   ANYHIT: returns true when an accepted hit with world distance <= limit exists.
+//   BRUTE : ignore the LBVH and test every primitive (debug / parity aid).
+template <bool ANYHIT, bool BRUTE, bool COUNT>
+__device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool reverse, double limit, Best& best,
+                                         WorkCounters& wc) {
+    best.geom = -1; best.face = -1; best.dobj = 0.0; best.wd = 0.0;
+    ObjRay R;
+    R.geom = -1; R.box_ok = 1;
+    if (BRUTE) {
+        for (int i = 0; i < S.num_all; i++)
+            if (test_prim<ANYHIT, COUNT>(S, __ldg(S.all_prims + i), o, d, reverse, limit, R, best, wc)) return true;
+        return false;
+    }
+    for (int i = 0; i < S.num_flat; i++)
+        if (test_prim<ANYHIT, COUNT>(S, __ldg(S.flat + i), o, d, reverse, limit, R, best, wc)) return true;
+    if (S.num_bvh_prims == 0) return false;
+    if (S.num_bvh_prims == 1)
+        return test_prim<ANYHIT, COUNT>(S, S.single_leaf, o, d, reverse, limit, R, best, wc);
+
+    const FRay fr = make_fray(o, d);
+    const float INF = __int_as_float(0x7f800000);
+    // prune limit in FP32, rounded up with slack; shrinks as closer hits are found
+    auto flimit = [&](double x) -> float {
+        if (!(x < 3.0e38)) return INF;
+        return __double2float_ru(x) * 1.00001f + 1e-30f;
+    };
+    float tlim = ANYHIT ? flimit(limit) : INF;
+    int stack[RT_STACK];
+    int sp = 0;
+    int node = 0;
+    while (true) {
+        const BvhNode* __restrict__ nptr = S.nodes + node;
+        float4 na = __ldg(&nptr->a), nb = __ldg(&nptr->b), nc = __ldg(&nptr->c);
+        int4 nd = __ldg(&nptr->d);
+        if (COUNT) wc.nodes += 2;
+        float tl = slab(fr, na.x, na.y, na.z, na.w, nb.x, nb.y, tlim);
+        float tr = slab(fr, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, tlim);
+        int first = nd.x, second = nd.y;
+        float tf = tl, ts = tr;
+        if (tr < tl) { first = nd.y; second = nd.x; tf = tr; ts = tl; }
+        int next = -1;
+        bool have_next = false;
+        // near child
+        if (tf < INF) {
+            if (first < 0) {
+                if (test_prim<ANYHIT, COUNT>(S, ~first, o, d, reverse, limit, R, best, wc)) return true;
+                if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
+            } else { next = first; have_next = true; }
+        }
+        if (ts < INF && ts <= tlim) {
+            if (second < 0) {
+                if (test_prim<ANYHIT, COUNT>(S, ~second, o, d, reverse, limit, R, best, wc)) return true;
+                if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
+            } else if (have_next) {
+                if (sp < RT_STACK) stack[sp++] = second;   // depth guard: LBVH over 30-bit codes stays far below
+            } else { next = second; have_next = true; }
+        }
+        if (have_next) { node = next; continue; }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return false;
+}
+
+}  // namespace rt

@@ -1,0 +1,394 @@
+// rt_kernels.cuh — the wavefront kernels that replace the reference's recursion:
+//   k_raygen    src/scene.cpp:26-30 + Camera::calculateViewingRay src/rtbase.h:74-84
+//   k_trace     Scene::castRay src/scene.cpp:142-167 (closest hit) -> compacted hit queue
+//   k_shade     Scene::traceRay src/scene.cpp:72-85 (normal, ambient) and :114-136 (bounce spawn)
+//   k_shadow    Scene::traceRay src/scene.cpp:86-107 (one thread per hit x shadow light)
+//   k_resolve   src/scene.cpp:31 (pixel store) + optional src/writers.cpp:7 quantisation
+// The recursion becomes an iterative bounce loop: a queued ray carries its pixel, the RGB
+// weight accumulated along its path (product of kr; refraction weight is 1,
+// src/scene.cpp:127,134), the remaining depth and the fromInside flag.  Queues are
+// compacted with warp-ballot + prefix-popcount appends.
+#pragma once
+#include "rt_device.cuh"
+
+namespace rt {
+
+#define RT_BLOCK 128
+
+// Ray queue, SoA over `cap` slots.
+struct RayQ {
+    double* f;     // 9 fields: ox oy oz dx dy dz wr wg wb
+    int* pixel;    // framebuffer slot, -1 = inactive
+    int* meta;     // depth | inside << 8
+    size_t cap;
+    __device__ __forceinline__ double& fld(int k, size_t i) const { return f[(size_t)k * cap + i]; }
+};
+// Hit queue (compacted): P N V W + dist, SoA over `cap` slots.
+struct HitQ {
+    double* f;     // 13 fields: P(3) N(3) V(3) W(3) dist
+    int* pixel;
+    int* geom;
+    int* meta;
+    size_t cap;
+    __device__ __forceinline__ double& fld(int k, size_t i) const { return f[(size_t)k * cap + i]; }
+};
+
+// device counters
+enum { CTR_HITS = 0, CTR_NEXT = 1, CTR_DEGENERATE = 2, CTR_NODES = 3, CTR_TRIS = 4, CTR_SPHERES = 5, CTR_COUNT = 8 };
+
+struct FrameInfo {
+    int width, height;
+    int tiles_x, tiles_y;
+    const int* tile_ids;   // [local tile] -> global tile index (ty * tiles_x + tx)
+};
+
+__device__ __forceinline__ bool slot_to_pixel(const FrameInfo& F, long long slot, int& px, int& py) {
+    int lt = (int)(slot / RT_TILE_PIXELS), j = (int)(slot % RT_TILE_PIXELS);
+    int gt = __ldg(F.tile_ids + lt);
+    int tx = gt % F.tiles_x, ty = gt / F.tiles_x;
+    int w = j >> 5, l = j & 31;                     // one warp = an 8x4 pixel block
+    int x = (w & 3) * 8 + (l & 7), y = (w >> 2) * 4 + (l >> 3);
+    px = tx * RT_TILE_W + x;
+    py = ty * RT_TILE_H + y;
+    return px < F.width && py < F.height;
+}
+
+// warp-aggregated append: returns the slot for threads with flag set
+__device__ __forceinline__ unsigned warp_append(bool flag, unsigned long long* counter) {
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    unsigned base = 0;
+    if (m) {
+        int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        if (lane == leader) base = (unsigned)atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        base += __popc(m & ((1u << lane) - 1u));
+    }
+    return base;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void flush_work(const WorkCounters& wc, unsigned long long* ctr) {
+    if (!COUNT) return;
+    unsigned long long a = wc.nodes, b = wc.tris, c = wc.spheres;
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(ctr + CTR_NODES, a);
+        atomicAdd(ctr + CTR_TRIS, b);
+        atomicAdd(ctr + CTR_SPHERES, c);
+    }
+}
+
+__global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long long first_slot, int n, int depth,
+                                                      RayQ q) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long slot = first_slot + i;
+    int px, py;
+    if (!slot_to_pixel(F, slot, px, py)) { q.pixel[i] = -1; return; }
+    double rowFrac = (py + 0.5) / F.height, colFrac = (px + 0.5) / F.width;
+    const DCamera& c = S.cam;
+    d3 LR = mk3(c.lr[0], c.lr[1], c.lr[2]), UR = mk3(c.ur[0], c.ur[1], c.ur[2]);
+    d3 LL = mk3(c.ll[0], c.ll[1], c.ll[2]), UL = mk3(c.ul[0], c.ul[1], c.ul[2]);
+    d3 E = mk3(c.eye[0], c.eye[1], c.eye[2]);
+    d3 right = rowFrac * LR + (1.0 - rowFrac) * UR;
+    d3 left = rowFrac * LL + (1.0 - rowFrac) * UL;
+    d3 ip = colFrac * right + (1.0 - colFrac) * left;
+    d3 raw = ip - E;
+    bool ok = !(raw.x == 0 && raw.y == 0 && raw.z == 0);   // Ray ctor would throw (src/rtbase.h:19-20)
+    d3 d = ok ? ray_normalize(raw) : raw;
+    q.fld(0, i) = E.x; q.fld(1, i) = E.y; q.fld(2, i) = E.z;
+    q.fld(3, i) = d.x; q.fld(4, i) = d.y; q.fld(5, i) = d.z;
+    q.fld(6, i) = 1.0; q.fld(7, i) = 1.0; q.fld(8, i) = 1.0;
+    q.pixel[i] = ok ? (int)slot : -1;
+    q.meta[i] = depth;
+}
+
+// Closest hit for every queued ray; hits are appended (compacted) to the hit queue.
+// ids_geom/ids_face (optional, indexed by framebuffer slot) receive the hit ids.
+template <bool BRUTE, bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RayQ q, size_t off, int n, HitQ h,
+                                                     unsigned long long* ctr, int* ids_geom, int* ids_face) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = off + (size_t)t;
+    bool active = t < n;
+    int pixel = active ? q.pixel[i] : -1;
+    active = active && pixel >= 0;
+    Best best;
+    best.geom = -1;
+    WorkCounters wc = {0, 0, 0};
+    d3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
+    int meta = 0;
+    if (active) {
+        o = mk3(q.fld(0, i), q.fld(1, i), q.fld(2, i));
+        d = mk3(q.fld(3, i), q.fld(4, i), q.fld(5, i));
+        meta = q.meta[i];
+        cast_ray<false, BRUTE, COUNT>(S, o, d, (meta >> 8) & 1, 0.0, best, wc);
+        if (ids_geom) { ids_geom[pixel] = best.geom; ids_face[pixel] = best.face; }
+    }
+    bool hit = active && best.geom >= 0;
+    unsigned slot = warp_append(hit, ctr + CTR_HITS);
+    if (hit) {
+        h.fld(0, slot) = best.P.x; h.fld(1, slot) = best.P.y; h.fld(2, slot) = best.P.z;
+        h.fld(3, slot) = best.N.x; h.fld(4, slot) = best.N.y; h.fld(5, slot) = best.N.z;
+        h.fld(6, slot) = d.x; h.fld(7, slot) = d.y; h.fld(8, slot) = d.z;
+        h.fld(9, slot) = q.fld(6, i); h.fld(10, slot) = q.fld(7, i); h.fld(11, slot) = q.fld(8, i);
+        h.fld(12, slot) = best.wd;
+        h.pixel[slot] = pixel;
+        h.geom[slot] = best.geom;
+        h.meta[slot] = meta;
+    }
+    flush_work<COUNT>(wc, ctr);
+}
+
+// --intersection-only: pixel = 1/dist^2 on all channels (src/scene.cpp:69-70)
+__global__ void __launch_bounds__(RT_BLOCK) k_shade_io(HitQ h, const unsigned long long* ctr, double* fb,
+                                                        unsigned long long* maxbits) {
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (j < (unsigned)ctr[CTR_HITS]) {
+        double dist = h.fld(12, j);
+        v = 1.0 / (dist * dist);
+        size_t p = (size_t)h.pixel[j] * 3;
+        fb[p] = v; fb[p + 1] = v; fb[p + 2] = v;
+    }
+    // non-negative doubles order like their bit patterns
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_down_sync(0xffffffffu, b, o);
+        b = x > b ? x : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(maxbits, b);
+}
+
+__global__ void k_divide(double* fb, size_t n, const unsigned long long* maxbits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fb[i] = fb[i] / __longlong_as_double((long long)*maxbits);
+}
+
+// Normal fix-up, ambient term, and the bounce spawn.
+__global__ void __launch_bounds__(RT_BLOCK) k_shade(DScene S, HitQ h, unsigned long long* ctr, RayQ next, double* fb) {
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = j < (unsigned)ctr[CTR_HITS];
+    bool want_t = false, want_r = false;
+    d3 P = mk3(0, 0, 0), Td = P, Rd = P;
+    double W[3] = {0, 0, 0}, kr[3] = {0, 0, 0};
+    int pixel = 0, depth = 0, inside = 0;
+    unsigned degenerate = 0;
+    if (active) {
+        P = mk3(h.fld(0, j), h.fld(1, j), h.fld(2, j));
+        d3 N = mk3(h.fld(3, j), h.fld(4, j), h.fld(5, j));
+        d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
+        W[0] = h.fld(9, j); W[1] = h.fld(10, j); W[2] = h.fld(11, j);
+        pixel = h.pixel[j];
+        int meta = h.meta[j];
+        depth = meta & 0xff;
+        inside = (meta >> 8) & 1;
+        const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
+        if (inside) N = -N;                                   // src/scene.cpp:72-73
+        N = inplace_normalize(N);                             // src/scene.cpp:75
+        h.fld(3, j) = N.x; h.fld(4, j) = N.y; h.fld(5, j) = N.z;
+        // ambient lights (src/scene.cpp:80-84)
+        if (S.num_alights > 0) {
+            double c[3] = {0, 0, 0};
+            for (int a = 0; a < S.num_alights; a++)
+                for (int k = 0; k < 3; k++) c[k] += 1.0 * S.alights[a].color[k] * m->ka[k];
+            for (int k = 0; k < 3; k++) atomicAdd(fb + (size_t)pixel * 3 + k, W[k] * c[k]);
+        }
+        // bounce (src/scene.cpp:114-136)
+        kr[0] = m->kr[0]; kr[1] = m->kr[1]; kr[2] = m->kr[2];
+        bool has_kr = m->has_kr != 0;
+        if (depth > 0) {
+            if (m->has_kt) {
+                double n = m->ior;
+                if (!inside) n = 1.0 / n;
+                double cosI = dot4(N, V);
+                double sinT2 = n * n * (1.0 - cosI * cosI);
+                if (sinT2 > 1.0) {
+                    kr[0] = kr[1] = kr[2] = 1.0;              // total internal reflection
+                    has_kr = true;
+                } else {
+                    d3 T = n * V - (n * cosI + sqrt(1.0 - sinT2)) * N;
+                    if (T.x == 0 && T.y == 0 && T.z == 0) degenerate++;
+                    else { Td = ray_normalize(T); want_t = true; }
+                }
+            }
+            if (has_kr) {
+                d3 Rv = V - (2 * dot4(N, V)) * N;
+                if (Rv.x == 0 && Rv.y == 0 && Rv.z == 0) degenerate++;
+                else { Rd = ray_normalize(Rv); want_r = true; }
+            }
+        }
+    }
+    unsigned st = warp_append(want_t, ctr + CTR_NEXT);
+    if (want_t) {
+        next.fld(0, st) = P.x; next.fld(1, st) = P.y; next.fld(2, st) = P.z;
+        next.fld(3, st) = Td.x; next.fld(4, st) = Td.y; next.fld(5, st) = Td.z;
+        next.fld(6, st) = W[0]; next.fld(7, st) = W[1]; next.fld(8, st) = W[2];   // weight 1, not kt
+        next.pixel[st] = pixel;
+        next.meta[st] = (depth - 1) | ((inside ^ 1) << 8);
+    }
+    unsigned sr = warp_append(want_r, ctr + CTR_NEXT);
+    if (want_r) {
+        next.fld(0, sr) = P.x; next.fld(1, sr) = P.y; next.fld(2, sr) = P.z;
+        next.fld(3, sr) = Rd.x; next.fld(4, sr) = Rd.y; next.fld(5, sr) = Rd.z;
+        next.fld(6, sr) = W[0] * kr[0]; next.fld(7, sr) = W[1] * kr[1]; next.fld(8, sr) = W[2] * kr[2];
+        next.pixel[sr] = pixel;
+        next.meta[sr] = (depth - 1) | (inside << 8);
+    }
+    if (degenerate) atomicAdd(ctr + CTR_DEGENERATE, (unsigned long long)degenerate);
+}
+
+// One thread per (hit, shadow light): occlusion query + Phong terms of that light.
+template <bool BRUTE, bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK) k_shadow(DScene S, HitQ h, unsigned long long* ctr, double* fb) {
+    unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nsl = (unsigned)S.num_slights;
+    WorkCounters wc = {0, 0, 0};
+    if (t < ctr[CTR_HITS] * nsl) {
+        unsigned j = (unsigned)(t / nsl), li = (unsigned)(t % nsl);
+        const DLight* l = S.slights + li;
+        d3 P = mk3(h.fld(0, j), h.fld(1, j), h.fld(2, j));
+        d3 N = mk3(h.fld(3, j), h.fld(4, j), h.fld(5, j));
+        d3 lv = mk3(l->v[0], l->v[1], l->v[2]);
+        const bool point = l->type == RT_LIGHT_POINT;
+        d3 toL = point ? lv - P : -lv;                        // src/lights.h:34-37,50-53
+        if (toL.x == 0 && toL.y == 0 && toL.z == 0) {
+            atomicAdd(ctr + CTR_DEGENERATE, 1ull);            // reference would abort (src/rtbase.h:19-20)
+        } else {
+            d3 L = ray_normalize(toL);
+            double ndl = dot4(N, L);
+            bool lrev = ndl < 0;                              // src/scene.cpp:88
+            const double INF = __longlong_as_double(0x7ff0000000000000ll);
+            double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
+            int inside = (h.meta[j] >> 8) & 1;
+            Best best;
+            bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc);
+            if (!occluded) {
+                const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
+                d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
+                double att[3];
+                if (point) {
+                    double f = pow(dL, -l->falloff);          // src/lights.h:23-25
+                    for (int k = 0; k < 3; k++) att[k] = f * l->color[k];
+                } else {
+                    for (int k = 0; k < 3; k++) att[k] = l->color[k];
+                }
+                double di = ndl < 0.0 ? 0.0 : ndl;            // std::max(N.L, 0.0)
+                d3 R = (2 * ndl) * N - L;                     // src/scene.cpp:101-102
+                double mvr = -dot4(V, R);
+                double si = pow(mvr < 0.0 ? 0.0 : mvr, m->sp);
+                int pixel = h.pixel[j];
+                for (int k = 0; k < 3; k++) {
+                    double w = h.fld(9 + k, j);
+                    double c = w * (di * att[k] * m->kd[k]) + w * (si * att[k] * m->ks[k]);
+                    atomicAdd(fb + (size_t)pixel * 3 + k, c);
+                }
+            }
+        }
+    }
+    flush_work<COUNT>(wc, ctr);
+}
+
+// Framebuffer slot order -> output.  full = row-major frame (tile_world == 1), otherwise
+// the packed tile layout is kept.  QUANT applies src/writers.cpp:7.
+__device__ __forceinline__ unsigned char quantize(double v) {
+    v = (1.0 < v) ? 1.0 : v;
+    v = (v < 0.0) ? 0.0 : v;
+    if (v != v) v = 0.0;
+    return (unsigned char)(int)(v * 255.0);
+}
+template <bool QUANT>
+__global__ void k_resolve(FrameInfo F, const double* __restrict__ fb, long long nslots, int full, void* out) {
+    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    int px, py;
+    bool inside = slot_to_pixel(F, slot, px, py);
+    size_t dst;
+    if (full) {
+        if (!inside) return;
+        dst = ((size_t)py * F.width + px) * 3;
+    } else {
+        dst = (size_t)slot * 3;
+    }
+    for (int k = 0; k < 3; k++) {
+        double v = inside ? fb[(size_t)slot * 3 + k] : 0.0;
+        if (QUANT) ((unsigned char*)out)[dst + k] = quantize(v);
+        else ((double*)out)[dst + k] = v;
+    }
+}
+
+// Gathered packed tiles (rank-major, each rank padded to max_tiles) -> row-major frame.
+template <typename T>
+__global__ void k_unpack(int width, int height, int tiles_x, int world, long long max_tiles,
+                         const int* __restrict__ rank_row_start /*[world][tiles_y+1]*/, int tiles_y,
+                         const T* __restrict__ packed, T* __restrict__ frame) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)width * height) return;
+    int px = (int)(i % width), py = (int)(i / width);
+    int tx = px / RT_TILE_W, ty = py / RT_TILE_H;
+    int rank = (tx + ty) % world;
+    int first_tx = ((rank - ty) % world + world) % world;
+    long long lt = rank_row_start[rank * (tiles_y + 1) + ty] + (tx - first_tx) / world;
+    int x = px % RT_TILE_W, y = py % RT_TILE_H;
+    int w = (y / 4) * 4 + (x / 8), l = (y % 4) * 8 + (x % 8);
+    long long slot = ((long long)rank * max_tiles + lt) * RT_TILE_PIXELS + w * 32 + l;
+    for (int k = 0; k < 3; k++) frame[i * 3 + k] = packed[slot * 3 + k];
+}
+
+// per-ray query (rt_cast_rays): dir normalised like the Ray ctor
+template <bool BRUTE>
+__global__ void __launch_bounds__(RT_BLOCK) k_query(DScene S, long long n, const double* __restrict__ org,
+                                                     const double* __restrict__ dir,
+                                                     const unsigned char* __restrict__ reverse, int* geom, int* face,
+                                                     double* dist, double* point, double* normal) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 o = mk3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
+    d3 raw = mk3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    Best best;
+    best.geom = -1; best.face = -1; best.wd = 0; best.P = mk3(0, 0, 0); best.N = mk3(0, 0, 0);
+    WorkCounters wc = {0, 0, 0};
+    if (raw.x == 0 && raw.y == 0 && raw.z == 0) {
+        best.geom = -2;
+    } else {
+        cast_ray<false, BRUTE, false>(S, o, ray_normalize(raw), reverse ? reverse[i] != 0 : false, 0.0, best, wc);
+    }
+    bool hit = best.geom >= 0;
+    if (geom) geom[i] = best.geom;
+    if (face) face[i] = hit ? best.face : -1;
+    if (dist) dist[i] = hit ? best.wd : 0.0;
+    if (point) { point[3 * i] = hit ? best.P.x : 0; point[3 * i + 1] = hit ? best.P.y : 0; point[3 * i + 2] = hit ? best.P.z : 0; }
+    if (normal) { normal[3 * i] = hit ? best.N.x : 0; normal[3 * i + 1] = hit ? best.N.y : 0; normal[3 * i + 2] = hit ? best.N.z : 0; }
+}
+
+// Raw faces (3 points / 3 normals, 9 doubles each) -> 80-byte device records.
+__global__ void k_pack_faces(long long nf, const double* __restrict__ pts, const double* __restrict__ nrm,
+                             const int* __restrict__ face_geom, const int* __restrict__ face_local,
+                             double2* __restrict__ out_p, double2* __restrict__ out_n) {
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const double* p = pts + 9 * f;
+    const double* n = nrm + 9 * f;
+    d3 p0 = mk3(p[0], p[1], p[2]), p1 = mk3(p[3], p[4], p[5]), p2 = mk3(p[6], p[7], p[8]);
+    d3 va = p1 - p0, vb = p2 - p0;    // the per-ray subtractions of src/geometry.cpp:80-81, done once
+    double aux = __hiloint2double(face_local[f], face_geom[f]);
+    double2* q = out_p + f * RT_FACE_D2;
+    q[0] = make_double2(p0.x, p0.y);
+    q[1] = make_double2(p0.z, va.x);
+    q[2] = make_double2(va.y, va.z);
+    q[3] = make_double2(vb.x, vb.y);
+    q[4] = make_double2(vb.z, aux);
+    double2* m = out_n + f * RT_FACE_D2;
+    m[0] = make_double2(n[0], n[1]);
+    m[1] = make_double2(n[2], n[3]);
+    m[2] = make_double2(n[4], n[5]);
+    m[3] = make_double2(n[6], n[7]);
+    m[4] = make_double2(n[8], 0.0);
+}
+
+}  // namespace rt

@@ -1,0 +1,29 @@
+// options.h — command-line surface of `as2`, identical to the reference's
+// (src/options.h:5-30, src/options.cpp:7-90): -t/--threads, -w/--width, -h/--height
+// (-h is HEIGHT, not help), -o/--output, --bdepth, --intersection-only, --help,
+// positional .rti files; one global instance `programOptions` that the render path
+// reads, exactly as src/scene.cpp:31,39,50,69 do.  Extra (ours): --gpus N.
+#pragma once
+#include <string>
+#include <vector>
+
+namespace as2 {
+
+class Options {
+public:
+    bool parseCommandLine(int argc, char* argv[]);
+    void printHelp(const char* prog);
+
+    std::vector<std::string> inputFilenames_;
+    std::string outputFilename_;
+    int renderThreadsCount_ = 1;   // accepted for compatibility; the GPU path ignores it
+    int renderWidth_ = 500;
+    int renderHeight_ = 500;
+    int bounceDepth_ = 10;
+    bool intersectionOnly_ = false;
+    bool bruteForce_ = false;      // --brute-force: debug aid, skips the LBVH
+};
+
+extern Options programOptions;
+
+}  // namespace as2
