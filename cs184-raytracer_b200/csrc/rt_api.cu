@@ -40,10 +40,33 @@ int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e_));                                               \
     } while (0)
 
+// After every kernel launch: configuration errors surface immediately (no sync); with
+// RT_DEBUG_SYNC=1 in the environment the stream is also synchronised so a faulting kernel
+// is reported by name.
+static bool debug_sync() {
+    static int v = -1;
+    if (v < 0) v = getenv("RT_DEBUG_SYNC") ? 1 : 0;
+    return v == 1;
+}
+#define LAUNCHED(name, st)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = cudaPeekAtLastError();                                                 \
+        if (e_ == cudaSuccess && debug_sync()) e_ = cudaStreamSynchronize(st);                  \
+        if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "kernel %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void release() {
         if (p) cudaFree(p);
@@ -352,6 +375,7 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
         k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p.p, raw_n.p, fg.p, fl.p,
                                                                   ctx->face_pts.p, ctx->face_nrm.p);
         launches++;
+        LAUNCHED("k_pack_faces", st);
         CU(cudaStreamSynchronize(st));
     }
     CU(cudaStreamSynchronize(st));
@@ -437,17 +461,22 @@ int ensure_level(rt_context* ctx, int level) {
 }
 
 template <bool BRUTE, bool COUNT>
-void launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h) {
+int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h) {
     k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, h, J.ctx->ctr.p,
                                                                             J.ids_geom, J.ids_face);
+    J.launches++;
+    LAUNCHED("k_trace", J.st);
+    return RT_OK;
 }
 template <bool BRUTE, bool COUNT>
-void launch_shadow(RenderJob& J, int n, HitQ h) {
+int launch_shadow(RenderJob& J, int n, HitQ h) {
     unsigned long long threads = (unsigned long long)n * (unsigned)J.ctx->S.num_slights;
-    if (!threads) return;
+    if (!threads) return RT_OK;
     k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, J.st>>>(J.ctx->S, h, J.ctx->ctr.p,
                                                                                                  J.ctx->fb.p);
     J.launches++;
+    LAUNCHED("k_shadow", J.st);
+    return RT_OK;
 }
 
 // Process n rays sitting in level `level`'s queue (and, recursively, everything they spawn).
@@ -466,14 +495,16 @@ int process_level(RenderJob& J, int level, size_t n) {
         const int m = (int)std::min(maxchunk, n - off);
         RayQ q = level_queue(ctx, level);
         CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
-        if (J.brute) { if (J.count) launch_trace<true, true>(J, q, off, m, h); else launch_trace<true, false>(J, q, off, m, h); }
-        else { if (J.count) launch_trace<false, true>(J, q, off, m, h); else launch_trace<false, false>(J, q, off, m, h); }
-        J.launches++;
+        int lrc;
+        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, h) : launch_trace<true, false>(J, q, off, m, h);
+        else lrc = J.count ? launch_trace<false, true>(J, q, off, m, h) : launch_trace<false, false>(J, q, off, m, h);
+        if (lrc != RT_OK) return lrc;
         if (ids_only) continue;
         const unsigned blocks = (unsigned)((m + RT_BLOCK - 1) / RT_BLOCK);
         if (io) {
             k_shade_io<<<blocks, RT_BLOCK, 0, J.st>>>(h, ctx->ctr.p, ctx->fb.p, J.maxbits);
             J.launches++;
+            LAUNCHED("k_shade_io", J.st);
             continue;
         }
         const bool last_level = level >= J.p->bounce_depth;
@@ -485,8 +516,10 @@ int process_level(RenderJob& J, int level, size_t n) {
         }
         k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, ctx->ctr.p, next, ctx->fb.p);
         J.launches++;
-        if (J.brute) { if (J.count) launch_shadow<true, true>(J, m, h); else launch_shadow<true, false>(J, m, h); }
-        else { if (J.count) launch_shadow<false, true>(J, m, h); else launch_shadow<false, false>(J, m, h); }
+        LAUNCHED("k_shade", J.st);
+        if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h) : launch_shadow<true, false>(J, m, h);
+        else lrc = J.count ? launch_shadow<false, true>(J, m, h) : launch_shadow<false, false>(J, m, h);
+        if (lrc != RT_OK) return lrc;
         CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, J.st));
         CU(cudaStreamSynchronize(J.st));
         const unsigned long long nhits = ctx->h_ctr[CTR_HITS], nnext = ctx->h_ctr[CTR_NEXT];
@@ -568,6 +601,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         const int n = (int)std::min<long long>((long long)maxchunk, nslots - first);
         k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0));
         J.launches++;
+        LAUNCHED("k_raygen", st);
         rc = process_level(J, 0, (size_t)n);
         if (rc != RT_OK) return rc;
         if (cb) {
@@ -580,6 +614,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         // all-reduces the max across ranks first (rt_io_get_max / rt_io_normalize)
         k_divide<<<(unsigned)(((size_t)nslots * 3 + 255) / 256), 256, 0, st>>>(ctx->fb.p, (size_t)nslots * 3, J.maxbits);
         J.launches++;
+        LAUNCHED("k_divide", st);
     }
     CU(cudaEventRecord(ctx->ev1, st));
     CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * CTR_COUNT, cudaMemcpyDeviceToHost, st));
@@ -615,7 +650,7 @@ int resolve_to(rt_context* ctx, const rt_params* p, void* d_out, cudaStream_t st
     F.tile_ids = ctx->tile_ids.p;
     k_resolve<QUANT><<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(F, ctx->fb.p, nslots, p->tile_world == 1 ? 1 : 0, d_out);
     ctx->stats.kernel_launches++;
-    CU(cudaGetLastError());
+    LAUNCHED("k_resolve", st);
     return RT_OK;
 }
 
