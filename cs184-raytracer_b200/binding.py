@@ -25,6 +25,7 @@ RT_GEOM_SPHERE, RT_GEOM_TRI, RT_GEOM_MESH = 0, 1, 2
 RT_LIGHT_AMBIENT, RT_LIGHT_POINT, RT_LIGHT_DIRECTIONAL = 0, 1, 2
 RT_FLAG_BRUTE_FORCE = 1
 RT_FLAG_COUNT_WORK = 2
+RT_FLAG_TIME_KERNELS = 4
 RT_TILE_PIXELS = 32 * 32
 
 
@@ -66,12 +67,18 @@ class rt_params(C.Structure):
 
 class rt_stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
-                ("nodes_fetched", C.c_uint64), ("tris_tested", C.c_uint64), ("spheres_tested", C.c_uint64),
-                ("degenerate_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_upload", C.c_double),
-                ("ms_build", C.c_double), ("ms_trace", C.c_double), ("ms_readback", C.c_double)]
+                ("degenerate_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("nodes_fetched", C.c_uint64 * 2), ("tris_tested", C.c_uint64 * 2), ("spheres_tested", C.c_uint64 * 2),
+                ("hits", C.c_uint64), ("ms_kernel", C.c_double * 4), ("launches_kernel", C.c_uint64 * 4),
+                ("ms_upload", C.c_double), ("ms_build", C.c_double), ("ms_trace", C.c_double),
+                ("ms_readback", C.c_double), ("scene_bytes_h2d", C.c_uint64)]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
 
 
 # symbols include/rt_b200.h declares (checked by tests/test_abi_exports.py)
@@ -79,6 +86,7 @@ RT_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_scene_upload", "rt_render", "rt_render_rgb8",
     "rt_render_device", "rt_render_device_rgb8", "rt_tile_count", "rt_tile_count_total", "rt_tile_count_max",
     "rt_unpack_tiles_rgb8", "rt_unpack_tiles", "rt_primary_ids", "rt_cast_rays", "rt_get_stats",
+    "rt_microbench_gather", "rt_scene_device_bytes",
 ]
 
 _rt = None
@@ -118,6 +126,8 @@ def load_rt() -> C.CDLL:
         lib.rt_cast_rays.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(rt_stats)]
+        lib.rt_microbench_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+        lib.rt_scene_device_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _rt = lib
     return _rt
 
@@ -292,6 +302,17 @@ class Renderer:
         self._check(self.lib.rt_cast_rays(self._h, n, _ptr(org), _ptr(direction), _ptr(rev), flags, _ptr(geom), _ptr(face),
                                           _ptr(dist), _ptr(point), _ptr(normal)), "rt_cast_rays")
         return geom, face, dist, point, normal
+
+    def device_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.rt_scene_device_bytes(self._h, C.byref(a), C.byref(b)), "rt_scene_device_bytes")
+        return int(a.value), int(b.value)
+
+    def microbench_gather(self, array_bytes, loads_per_thread=64) -> float:
+        g = C.c_double()
+        self._check(self.lib.rt_microbench_gather(self._h, int(array_bytes), int(loads_per_thread), C.byref(g)),
+                    "rt_microbench_gather")
+        return float(g.value)
 
     def stats(self) -> dict:
         st = rt_stats()

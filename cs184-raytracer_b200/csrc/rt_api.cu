@@ -135,6 +135,10 @@ struct rt_context {
     unsigned long long* h_ctr = nullptr;    // pinned
     TileLayout tiles;
     rt_stats stats;
+    std::vector<cudaEvent_t> evpool;        // RT_FLAG_TIME_KERNELS: (start, stop) pairs
+    std::vector<int> evclass;
+    size_t evused = 0;
+    size_t node_bytes = 0, face_bytes = 0;
     rt_context() { memset(&S, 0, sizeof(S)); memset(&stats, 0, sizeof(stats)); }
 };
 
@@ -183,6 +187,7 @@ void rt_destroy(rt_context* ctx) {
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -418,6 +423,12 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1);
     cudaEventElapsedTime(&ms1, ctx->ev1, evb);
     cudaEventDestroy(evb);
+    ctx->node_bytes = bvh_codes.size() >= 2 ? sizeof(BvhNode) * (bvh_codes.size() - 1) : 0;
+    ctx->face_bytes = sizeof(double2) * RT_FACE_D2 * 2 * (size_t)s->num_faces;
+    ctx->stats.scene_bytes_h2d = sizeof(DGeom) * hg.size() + sizeof(DMat) * hm.size() +
+                                 sizeof(DLight) * (hsl.size() + hal.size()) +
+                                 sizeof(int) * (flat_codes.size() + all_codes.size() + bvh_codes.size()) +
+                                 (size_t)s->num_faces * (2 * 72 + 8);
     ctx->stats.ms_upload = ms0;
     ctx->stats.ms_build = ms1;
     ctx->stats.kernel_launches = (uint64_t)launches;
@@ -434,11 +445,37 @@ struct RenderJob {
     rt_context* ctx;
     const rt_params* p;
     cudaStream_t st;
-    bool brute, count;
+    bool brute, count, timed;
     int* ids_geom;
     int* ids_face;
     unsigned long long* maxbits;   // intersection-only
     uint64_t launches;
+};
+
+// RT_FLAG_TIME_KERNELS: a (start, stop) event pair around one launch of kernel class `cls`.
+struct LaunchTimer {
+    RenderJob& J;
+    size_t idx = 0;
+    bool on;
+    LaunchTimer(RenderJob& j, int cls) : J(j), on(j.timed) {
+        if (!on) return;
+        rt_context* c = J.ctx;
+        if (c->evused + 2 > c->evpool.size()) {
+            for (int k = 0; k < 2; k++) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                c->evpool.push_back(e);
+            }
+            c->evclass.resize(c->evpool.size() / 2);
+        }
+        idx = c->evused;
+        c->evclass[idx / 2] = cls;
+        c->evused += 2;
+        cudaEventRecord(c->evpool[idx], J.st);
+    }
+    ~LaunchTimer() {
+        if (on) cudaEventRecord(J.ctx->evpool[idx + 1], J.st);
+    }
 };
 
 RayQ level_queue(rt_context* ctx, int level) {
@@ -462,6 +499,7 @@ int ensure_level(rt_context* ctx, int level) {
 
 template <bool BRUTE, bool COUNT>
 int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h) {
+    LaunchTimer lt(J, 0);
     k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, h, J.ctx->ctr.p,
                                                                             J.ids_geom, J.ids_face);
     J.launches++;
@@ -472,6 +510,7 @@ template <bool BRUTE, bool COUNT>
 int launch_shadow(RenderJob& J, int n, HitQ h) {
     unsigned long long threads = (unsigned long long)n * (unsigned)J.ctx->S.num_slights;
     if (!threads) return RT_OK;
+    LaunchTimer lt(J, 2);
     k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, J.st>>>(J.ctx->S, h, J.ctx->ctr.p,
                                                                                                  J.ctx->fb.p);
     J.launches++;
@@ -502,6 +541,7 @@ int process_level(RenderJob& J, int level, size_t n) {
         if (ids_only) continue;
         const unsigned blocks = (unsigned)((m + RT_BLOCK - 1) / RT_BLOCK);
         if (io) {
+            LaunchTimer lt(J, 1);
             k_shade_io<<<blocks, RT_BLOCK, 0, J.st>>>(h, ctx->ctr.p, ctx->fb.p, J.maxbits);
             J.launches++;
             LAUNCHED("k_shade_io", J.st);
@@ -514,7 +554,10 @@ int process_level(RenderJob& J, int level, size_t n) {
             if (rc != RT_OK) return rc;
             next = level_queue(ctx, level + 1);
         }
-        k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, ctx->ctr.p, next, ctx->fb.p);
+        {
+            LaunchTimer lt(J, 1);
+            k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, ctx->ctr.p, next, ctx->fb.p);
+        }
         J.launches++;
         LAUNCHED("k_shade", J.st);
         if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h) : launch_shadow<true, false>(J, m, h);
@@ -523,6 +566,7 @@ int process_level(RenderJob& J, int level, size_t n) {
         CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, J.st));
         CU(cudaStreamSynchronize(J.st));
         const unsigned long long nhits = ctx->h_ctr[CTR_HITS], nnext = ctx->h_ctr[CTR_NEXT];
+        ctx->stats.hits += nhits;
         ctx->stats.rays_shadow += nhits * (unsigned long long)ctx->S.num_slights;
         ctx->stats.rays_secondary += nnext;
         if (nnext > 0) {
@@ -571,6 +615,8 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     J.ctx = ctx; J.p = p; J.st = st;
     J.brute = (p->flags & RT_FLAG_BRUTE_FORCE) != 0;
     J.count = (p->flags & RT_FLAG_COUNT_WORK) != 0;
+    J.timed = (p->flags & RT_FLAG_TIME_KERNELS) != 0;
+    ctx->evused = 0;
     J.ids_geom = nullptr; J.ids_face = nullptr;
     J.maxbits = ctx->ctr.p + CTR_COUNT;
     J.launches = 0;
@@ -583,8 +629,9 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         J.ids_face = ctx->ids_face.p;
     }
     rt_stats& stats = ctx->stats;
-    stats.rays_primary = stats.rays_shadow = stats.rays_secondary = 0;
-    stats.nodes_fetched = stats.tris_tested = stats.spheres_tested = stats.degenerate_rays = 0;
+    stats.rays_primary = stats.rays_shadow = stats.rays_secondary = stats.hits = stats.degenerate_rays = 0;
+    for (int k = 0; k < 2; k++) stats.nodes_fetched[k] = stats.tris_tested[k] = stats.spheres_tested[k] = 0;
+    for (int k = 0; k < 4; k++) { stats.ms_kernel[k] = 0; stats.launches_kernel[k] = 0; }
     CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * (CTR_COUNT + 1), st));
     if (p->intersection_only) {
         // std::numeric_limits<double>::min() (src/scene.cpp:51)
@@ -599,7 +646,10 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     const long long total_px = (long long)p->width * p->height;
     for (long long first = 0; first < nslots; first += (long long)maxchunk) {
         const int n = (int)std::min<long long>((long long)maxchunk, nslots - first);
-        k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0));
+        {
+            LaunchTimer lt(J, 3);
+            k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0));
+        }
         J.launches++;
         LAUNCHED("k_raygen", st);
         rc = process_level(J, 0, (size_t)n);
@@ -632,11 +682,20 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     stats.rays_primary = (uint64_t)prim;
     stats.degenerate_rays = ctx->h_ctr[CTR_DEGENERATE];
-    stats.rays_shadow -= 0;   // degenerate shadow rays are counted separately
-    stats.nodes_fetched = ctx->h_ctr[CTR_NODES];
-    stats.tris_tested = ctx->h_ctr[CTR_TRIS];
-    stats.spheres_tested = ctx->h_ctr[CTR_SPHERES];
+    stats.nodes_fetched[0] = ctx->h_ctr[CTR_NODES];
+    stats.tris_tested[0] = ctx->h_ctr[CTR_TRIS];
+    stats.spheres_tested[0] = ctx->h_ctr[CTR_SPHERES];
+    stats.nodes_fetched[1] = ctx->h_ctr[CTR_S_NODES];
+    stats.tris_tested[1] = ctx->h_ctr[CTR_S_TRIS];
+    stats.spheres_tested[1] = ctx->h_ctr[CTR_S_SPHERES];
     stats.kernel_launches = J.launches;
+    for (size_t k = 0; k + 1 < ctx->evused; k += 2) {
+        float kms = 0;
+        cudaEventElapsedTime(&kms, ctx->evpool[k], ctx->evpool[k + 1]);
+        int cls = ctx->evclass[k / 2];
+        stats.ms_kernel[cls] += kms;
+        stats.launches_kernel[cls]++;
+    }
     if (cb) cb((int)total_px, (int)total_px, user);
     return RT_OK;
 }
@@ -831,6 +890,42 @@ int rt_cast_rays(rt_context* ctx, int64_t n, const double* org, const double* di
     if (dist) CU(cudaMemcpy(dist, d_dist.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
     if (point) CU(cudaMemcpy(point, d_point.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost));
     if (normal) CU(cudaMemcpy(normal, d_normal.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_scene_device_bytes(rt_context* ctx, uint64_t* node_bytes, uint64_t* face_bytes) {
+    if (!ctx) return fail(RT_ERR_INVALID, "context is NULL");
+    if (node_bytes) *node_bytes = ctx->node_bytes;
+    if (face_bytes) *face_bytes = ctx->face_bytes;
+    return RT_OK;
+}
+
+int rt_microbench_gather(rt_context* ctx, uint64_t array_bytes, int loads_per_thread, double* gbs) {
+    if (!ctx || !gbs || loads_per_thread < 1) return fail(RT_ERR_INVALID, "rt_microbench_gather: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if (array_bytes < 64) array_bytes = 64;
+    const unsigned long long nrec = array_bytes / 32;
+    DevBuf<float4> data;
+    DevBuf<float> sink;
+    CU(data.ensure((size_t)nrec * 2));
+    CU(sink.ensure(1));
+    CU(cudaMemsetAsync(data.p, 0, (size_t)nrec * 32, ctx->stream));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 16, threads = 256;
+    k_gather_probe<<<blocks, threads, 0, ctx->stream>>>(data.p, nrec, loads_per_thread, sink.p);   // warm-up
+    LAUNCHED("k_gather_probe", ctx->stream);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_gather_probe<<<blocks, threads, 0, ctx->stream>>>(data.p, nrec, loads_per_thread, sink.p);
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (ms < best) best = ms;
+    }
+    *gbs = (double)blocks * threads * loads_per_thread * 32.0 / (best * 1e-3) / 1e9;
     return RT_OK;
 }
 

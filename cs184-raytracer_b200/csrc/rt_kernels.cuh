@@ -34,7 +34,12 @@ struct HitQ {
 };
 
 // device counters
-enum { CTR_HITS = 0, CTR_NEXT = 1, CTR_DEGENERATE = 2, CTR_NODES = 3, CTR_TRIS = 4, CTR_SPHERES = 5, CTR_COUNT = 8 };
+enum {
+    CTR_HITS = 0, CTR_NEXT = 1, CTR_DEGENERATE = 2,
+    CTR_NODES = 3, CTR_TRIS = 4, CTR_SPHERES = 5,          // closest-hit kernel
+    CTR_S_NODES = 6, CTR_S_TRIS = 7, CTR_S_SPHERES = 8,    // shadow kernel
+    CTR_COUNT = 10
+};
 
 struct FrameInfo {
     int width, height;
@@ -67,7 +72,7 @@ __device__ __forceinline__ unsigned warp_append(bool flag, unsigned long long* c
 }
 
 template <bool COUNT>
-__device__ __forceinline__ void flush_work(const WorkCounters& wc, unsigned long long* ctr) {
+__device__ __forceinline__ void flush_work(const WorkCounters& wc, unsigned long long* ctr /* -> nodes slot */) {
     if (!COUNT) return;
     unsigned long long a = wc.nodes, b = wc.tris, c = wc.spheres;
     for (int o = 16; o > 0; o >>= 1) {
@@ -76,9 +81,9 @@ __device__ __forceinline__ void flush_work(const WorkCounters& wc, unsigned long
         c += __shfl_down_sync(0xffffffffu, c, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(ctr + CTR_NODES, a);
-        atomicAdd(ctr + CTR_TRIS, b);
-        atomicAdd(ctr + CTR_SPHERES, c);
+        atomicAdd(ctr + 0, a);
+        atomicAdd(ctr + 1, b);
+        atomicAdd(ctr + 2, c);
     }
 }
 
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RayQ q, size_t off
         h.geom[slot] = best.geom;
         h.meta[slot] = meta;
     }
-    flush_work<COUNT>(wc, ctr);
+    flush_work<COUNT>(wc, ctr + CTR_NODES);
 }
 
 // --intersection-only: pixel = 1/dist^2 on all channels (src/scene.cpp:69-70)
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shadow(DScene S, HitQ h, unsigned 
             }
         }
     }
-    flush_work<COUNT>(wc, ctr);
+    flush_work<COUNT>(wc, ctr + CTR_S_NODES);
 }
 
 // Framebuffer slot order -> output.  full = row-major frame (tile_world == 1), otherwise
@@ -364,6 +369,21 @@ __global__ void __launch_bounds__(RT_BLOCK) k_query(DScene S, long long n, const
     if (dist) dist[i] = hit ? best.wd : 0.0;
     if (point) { point[3 * i] = hit ? best.P.x : 0; point[3 * i + 1] = hit ? best.P.y : 0; point[3 * i + 2] = hit ? best.P.z : 0; }
     if (normal) { normal[3 * i] = hit ? best.N.x : 0; normal[3 * i + 1] = hit ? best.N.y : 0; normal[3 * i + 2] = hit ? best.N.z : 0; }
+}
+
+// Node-bandwidth roofline probe: every thread issues `loads` independent 32-byte gathers
+// (two float4 __ldg of one 32-byte-aligned record) at hashed positions.
+__global__ void k_gather_probe(const float4* __restrict__ data, unsigned long long nrec, int loads, float* sink) {
+    unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long x = t * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    float acc = 0.f;
+    for (int i = 0; i < loads; i++) {
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+        unsigned long long r = x % nrec;
+        float4 a = __ldg(data + 2 * r), b = __ldg(data + 2 * r + 1);
+        acc += a.x + b.w;
+    }
+    if (acc == 123.456f) *sink = acc;
 }
 
 // Raw faces (3 points / 3 normals, 9 doubles each) -> 80-byte device records.

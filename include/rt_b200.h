@@ -121,6 +121,7 @@ typedef struct rt_scene {
 #define RT_FLAG_BRUTE_FORCE   1u  /* no LBVH: every ray tests every primitive (parity aid) */
 #define RT_FLAG_COUNT_WORK    2u  /* instrumented build of the same kernels: count nodes /
                                      primitives fetched for the roofline (slower)          */
+#define RT_FLAG_TIME_KERNELS  4u  /* bracket every launch with CUDA events (rt_stats.ms_kernel) */
 
 typedef struct rt_params {
     int32_t  width;              /* programOptions.renderWidth_   (src/options.h:13) */
@@ -143,15 +144,22 @@ typedef struct rt_stats {
     uint64_t rays_primary;     /* src/scene.cpp:65 from :31                   */
     uint64_t rays_shadow;      /* src/scene.cpp:91                            */
     uint64_t rays_secondary;   /* src/scene.cpp:127,134                       */
-    uint64_t nodes_fetched;    /* RT_FLAG_COUNT_WORK: 32-byte BVH boxes tested */
-    uint64_t tris_tested;      /* RT_FLAG_COUNT_WORK: exact FP64 face tests    */
-    uint64_t spheres_tested;   /* RT_FLAG_COUNT_WORK: exact sphere tests       */
     uint64_t degenerate_rays;  /* rays the reference would have aborted on (src/rtbase.h:14-22) */
     uint64_t kernel_launches;  /* kernels launched by the last render          */
+    /* RT_FLAG_COUNT_WORK: work done by the closest-hit kernel [0] and the shadow kernel [1] */
+    uint64_t nodes_fetched[2];   /* 32-byte BVH child boxes tested              */
+    uint64_t tris_tested[2];     /* exact FP64 face tests (80-byte records)     */
+    uint64_t spheres_tested[2];  /* exact sphere tests                          */
+    uint64_t hits;               /* shaded hits (each casts one shadow ray per non-ambient light) */
+    /* RT_FLAG_TIME_KERNELS: summed CUDA-event durations and launch counts per kernel class
+     * [0] k_trace  [1] k_shade  [2] k_shadow  [3] raygen/resolve/other */
+    double   ms_kernel[4];
+    uint64_t launches_kernel[4];
     double   ms_upload;        /* H2D scene + flatten (last rt_scene_upload)   */
     double   ms_build;         /* LBVH build (last rt_scene_upload)            */
     double   ms_trace;         /* device time of the last render (CUDA events) */
     double   ms_readback;      /* D2H of the result (host-buffer entry points) */
+    uint64_t scene_bytes_h2d;  /* bytes copied host->device by the last rt_scene_upload */
 } rt_stats;
 
 typedef struct rt_context rt_context;
@@ -215,6 +223,13 @@ int  rt_cast_rays(rt_context* ctx, int64_t n, const double* org, const double* d
                   int32_t* geom, int32_t* face, double* dist, double* point, double* normal);
 
 int  rt_get_stats(rt_context* ctx, rt_stats* out);
+
+/* Measured BVH-node-bandwidth roofline (BASELINE.json north_star): independent random
+ * 32-byte __ldg gathers over an array of `array_bytes` (use the scene's node-array size),
+ * `loads_per_thread` per thread over a full-chip grid.  Returns GB/s in *gbs. */
+int  rt_microbench_gather(rt_context* ctx, uint64_t array_bytes, int loads_per_thread, double* gbs);
+/* Size in bytes of the LBVH node array and of the face records of the uploaded scene. */
+int  rt_scene_device_bytes(rt_context* ctx, uint64_t* node_bytes, uint64_t* face_bytes);
 
 #ifdef __cplusplus
 }

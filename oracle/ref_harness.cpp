@@ -109,6 +109,91 @@ void* ref_scene_load(const char** files, int nfiles, char* err, int errlen) {
     return rs;
 }
 
+// Build the REFERENCE object graph from a flat descriptor (used for scenes that exist only
+// in memory, i.e. the synthetic benchmark scene): reference Sphere/Mesh/Light/Camera objects
+// are created through the reference's own classes; transforms go through
+// Transformable::forwardTransform so the reference computes its own inverse/determinant.
+// Lights and camera are handed over already transformed (identity transform on the objects).
+void* ref_scene_from_flat(const rt_scene* f, char* err, int errlen) {
+    RefScene* rs = new RefScene();
+    try {
+        auto xf_of = [](const double* m) {
+            Transform4d T = Transform4d::Identity();
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 4; c++) T.matrix()(r, c) = m[r * 4 + c];
+            return T;
+        };
+        auto P = [](const double* v) { return Vector4d(v[0], v[1], v[2], 1.0); };
+        auto C3 = [](const double* v) { return Color3d(v[0], v[1], v[2]); };
+        Camera cam;
+        cam.forwardTransform(Transform4d::Identity());
+        cam.eyePoint(P(f->camera.eye));
+        cam.lowerLeftPoint(P(f->camera.ll));
+        cam.lowerRightPoint(P(f->camera.lr));
+        cam.upperLeftPoint(P(f->camera.ul));
+        cam.upperRightPoint(P(f->camera.ur));
+        rs->scene.camera(cam);
+        for (int i = 0; i < f->num_lights; i++) {
+            const rt_light& l = f->lights[i];
+            Light* out;
+            if (l.type == RT_LIGHT_POINT) {
+                PointLight* pl = new PointLight();
+                pl->point(P(l.v));
+                pl->falloffExponent_ = l.falloff;
+                out = pl;
+            } else if (l.type == RT_LIGHT_DIRECTIONAL) {
+                DirectionalLight* dl = new DirectionalLight();
+                dl->direction(Vector4d(l.v[0], l.v[1], l.v[2], 0.0));
+                out = dl;
+            } else {
+                out = new AmbientLight();
+            }
+            out->forwardTransform(Transform4d::Identity());
+            out->color_ = C3(l.color);
+            rs->scene.addLight(std::unique_ptr<Light>(out));
+        }
+        for (int i = 0; i < f->num_geometries; i++) {
+            const rt_geometry& g = f->geometries[i];
+            const rt_material& m = f->materials[g.material];
+            Geometry* out;
+            if (g.type == RT_GEOM_SPHERE) {
+                Sphere* s = new Sphere();
+                s->center_ = P(g.center);
+                s->radius_ = (float)g.radius;
+                out = s;
+            } else {
+                Mesh* me = new Mesh();
+                me->faces_.resize((size_t)g.num_faces);
+                for (int64_t k = 0; k < g.num_faces; k++) {
+                    const double* fp = f->face_points + 9 * (g.first_face + k);
+                    const double* fn = f->face_normals + 9 * (g.first_face + k);
+                    for (int v = 0; v < 3; v++) {
+                        me->faces_[(size_t)k].points_[v] = Vector4d(fp[3 * v], fp[3 * v + 1], fp[3 * v + 2], 1.0);
+                        me->faces_[(size_t)k].normals_[v] = Vector4d(fn[3 * v], fn[3 * v + 1], fn[3 * v + 2], 0.0);
+                    }
+                }
+                if (g.type == RT_GEOM_MESH) me->updateBoundingBox();
+                out = me;
+            }
+            out->forwardTransform(xf_of(g.fwd));
+            out->material_.ambientColor_ = C3(m.ka);
+            out->material_.diffuseColor_ = C3(m.kd);
+            out->material_.specularColor_ = C3(m.ks);
+            out->material_.reflectiveColor_ = C3(m.kr);
+            out->material_.translucencyColor_ = C3(m.kt);
+            out->material_.specularCoefficient_ = m.sp;
+            out->material_.indexOfRefractivity_ = m.ior;
+            rs->scene.addGeometry(std::unique_ptr<Geometry>(out));
+        }
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        delete rs;
+        return nullptr;
+    }
+    prewarm(rs->scene);
+    return rs;
+}
+
 void ref_scene_free(void* h) { delete static_cast<RefScene*>(h); }
 
 int ref_num_geometries(void* h) { return (int)static_cast<RefScene*>(h)->scene.geometries_.size(); }
@@ -126,7 +211,10 @@ int ref_render(void* h, int width, int height, int depth, int intersection_only,
     const long total = (long)width * height;
     std::atomic<long> next(0);
     g_geomtests = 0;
-    const int blockSize = 2000;
+    // the reference hands out 2000-pixel blocks (src/scene.cpp:13); small sample frames get
+    // smaller blocks so that every thread has work (scheduling only, no effect on pixels)
+    long bs = total / ((long)threads * 4);
+    const int blockSize = (int)std::max(1L, std::min(2000L, bs));
     auto worker = [&]() {
         t_geomtests = 0;
         Camera& cam = scene.camera_;

@@ -304,7 +304,7 @@ static void camera_ray(const rt_scene* s, int width, int height, int r, int c, v
 typedef struct {
     const rt_scene* s; const rt_params* p;
     double* rgb; int32_t* geom; int32_t* face;
-    int64_t* next; int64_t total;
+    int64_t* next; int64_t total; int64_t block;
     counts_t cnt;
     pthread_mutex_t* mu;
 } job_t;
@@ -313,9 +313,9 @@ static void* worker(void* arg) {
     job_t* j = (job_t*)arg;
     const int W = j->p->width, H = j->p->height;
     for (;;) {
-        int64_t start = __atomic_fetch_add(j->next, 2000, __ATOMIC_RELAXED);
+        int64_t start = __atomic_fetch_add(j->next, j->block, __ATOMIC_RELAXED);
         if (start >= j->total) break;
-        int64_t end = start + 2000 < j->total ? start + 2000 : j->total;
+        int64_t end = start + j->block < j->total ? start + j->block : j->total;
         for (int64_t i = start; i < end; i++) {
             int r = (int)(i / W), c = (int)(i % W);
             v3 o, d;
@@ -339,8 +339,13 @@ int oracle_render(const rt_scene* s, const rt_params* p, double* rgb, int32_t* g
     if (threads > 256) threads = 256;
     int64_t next = 0, total = (int64_t)p->width * p->height;
     job_t jobs[256]; pthread_t th[256];
+    /* 2000-pixel blocks like src/scene.cpp:13, smaller on small frames so all threads work */
+    int64_t block = total / ((int64_t)threads * 4);
+    if (block > 2000) block = 2000;
+    if (block < 1) block = 1;
     for (int t = 0; t < threads; t++) {
         memset(&jobs[t], 0, sizeof(job_t));
+        jobs[t].block = block;
         jobs[t].s = s; jobs[t].p = p; jobs[t].rgb = rgb; jobs[t].geom = geom; jobs[t].face = face;
         jobs[t].next = &next; jobs[t].total = total;
         pthread_create(&th[t], NULL, worker, &jobs[t]);
