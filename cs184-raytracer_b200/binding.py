@@ -190,6 +190,7 @@ class HostScene:
             p = load_host().as2_scene_flatten(self._h, err, 512)
             if not p:
                 raise RtError(err.value.decode())
+            p._owner = self          # the descriptor points into memory owned by this scene
             self._flat = p
         return self._flat
 

@@ -345,8 +345,10 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
             else bvh_codes.push_back(simple_codes[k]);
         }
     }
+    const int n_simple_in_bvh = (int)bvh_codes.size();
     for (int code : all_codes)
         if ((code >> PRIM_KIND_SHIFT) == PRIM_FACE) bvh_codes.push_back(code);
+    const int group_sizes[2] = {n_simple_in_bvh, (int)bvh_codes.size() - n_simple_in_bvh};
 
     // ---- uploads ----
     CU(ctx->geoms.ensure((size_t)ng));
@@ -403,17 +405,20 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     S.num_all = (int)all_codes.size();
     S.num_bvh_prims = (int)bvh_codes.size();
     S.single_leaf = bvh_codes.size() == 1 ? bvh_codes[0] : 0;
+    S.shadow_mode = getenv("RT_SHADOW_MODE") ? atoi(getenv("RT_SHADOW_MODE")) : 3;
     CU(cudaEventRecord(ctx->ev1, st));
 
     // ---- LBVH ----
     if (ctx->nodes) { cudaFree(ctx->nodes); ctx->nodes = nullptr; }
     cudaEvent_t evb;
     CU(cudaEventCreate(&evb));
+    size_t node_count = 0;
     if (bvh_codes.size() >= 2) {
         float eye_abs = 0.f;
         for (int k = 0; k < 3; k++) eye_abs = fmaxf(eye_abs, (float)fabs(s->camera.eye[k]));
         char err[256] = "";
-        int brc = build_lbvh(S, ctx->bvh_prims.p, (int)bvh_codes.size(), eye_abs, st, &ctx->nodes, &launches, err, sizeof(err));
+        int brc = build_lbvh(S, ctx->bvh_prims.p, bvh_codes.data(), (int)bvh_codes.size(), group_sizes, 2, eye_abs, st,
+                             &ctx->nodes, &node_count, &launches, err, sizeof(err));
         if (brc != RT_OK) { cudaEventDestroy(evb); return fail(brc, "LBVH build: %s", err); }
     }
     S.nodes = ctx->nodes;
@@ -423,7 +428,7 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1);
     cudaEventElapsedTime(&ms1, ctx->ev1, evb);
     cudaEventDestroy(evb);
-    ctx->node_bytes = bvh_codes.size() >= 2 ? sizeof(BvhNode) * (bvh_codes.size() - 1) : 0;
+    ctx->node_bytes = sizeof(BvhNode) * node_count;
     ctx->face_bytes = sizeof(double2) * RT_FACE_D2 * 2 * (size_t)s->num_faces;
     ctx->stats.scene_bytes_h2d = sizeof(DGeom) * hg.size() + sizeof(DMat) * hm.size() +
                                  sizeof(DLight) * (hsl.size() + hal.size()) +

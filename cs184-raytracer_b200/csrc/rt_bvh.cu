@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "rt_bvh.h"
 
@@ -92,11 +93,16 @@ __global__ void k_morton(const float* __restrict__ lo, const float* __restrict__
                          const int* __restrict__ gbounds, uint32_t* __restrict__ keys, int* __restrict__ vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // Quantise all three axes with the SAME cell size (the largest centroid extent): cubic
+    // Morton cells.  Normalising each axis separately would spend as many bits on the thin
+    // axis of a 2.5-D scene (a height field) as on the long ones and cut it into "hills" and
+    // "valleys" whose boxes overlap everywhere.
     uint32_t q[3];
+    float ext = 0.f;
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, ord2f(gbounds[3 + a]) - ord2f(gbounds[a]));
     for (int a = 0; a < 3; a++) {
-        float cmin = ord2f(gbounds[a]), cmax = ord2f(gbounds[3 + a]);
+        float cmin = ord2f(gbounds[a]);
         float c = 0.5f * lo[3 * (size_t)i + a] + 0.5f * hi[3 * (size_t)i + a];
-        float ext = cmax - cmin;
         float u = ext > 0.f ? (c - cmin) / ext : 0.f;
         int v = (int)(u * 1024.f);
         q[a] = (uint32_t)min(max(v, 0), 1023);
@@ -265,7 +271,7 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __r
                              const float* __restrict__ plo, const float* __restrict__ phi,
                              const int* __restrict__ left, const int* __restrict__ right,
                              const float* __restrict__ ilo, const float* __restrict__ ihi,
-                             const int* __restrict__ gbounds, BvhNode* __restrict__ nodes) {
+                             const int* __restrict__ gbounds, BvhNode* __restrict__ nodes, int node_offset) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     // pad: a few FP32 ulps at the scene's largest coordinate (covers the slab test's rounding)
@@ -281,7 +287,7 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __r
             ref[k] = ~codes[p];
         } else {
             bl = ilo + 3 * (size_t)ch[k]; bh = ihi + 3 * (size_t)ch[k];
-            ref[k] = ch[k];
+            ref[k] = ch[k] + node_offset;
         }
         for (int a = 0; a < 3; a++) {
             float l = bl[a], h = bh[a];
@@ -294,7 +300,7 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __r
     nd.b = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
     nd.c = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
     nd.d = make_int4(ref[0], ref[1], 0, 0);
-    nodes[i] = nd;
+    nodes[node_offset + i] = nd;
 }
 
 #define CK(x)                                                                          \
@@ -306,9 +312,14 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __r
         }                                                                              \
     } while (0)
 
-int build_lbvh(const DScene& S, const int* d_codes, int n, float extra_abs, cudaStream_t stream,
-               BvhNode** out_nodes, int* launches, char* err, int errlen) {
+// One LBVH per primitive GROUP (e.g. spheres/`tri`s vs mesh faces), joined under a short
+// chain of super nodes: floating spheres mixed into a height-field's Morton order would
+// otherwise stretch the leaf-level boxes of the mesh over the whole air space.
+int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, const int* group_sizes, int ngroups,
+               float extra_abs, cudaStream_t stream, BvhNode** out_nodes, size_t* out_count, int* launches,
+               char* err, int errlen) {
     *out_nodes = nullptr;
+    *out_count = 0;
     float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
     int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
     int *left = nullptr, *right = nullptr, *pint = nullptr, *pleaf = nullptr, *flags = nullptr;
@@ -317,7 +328,21 @@ int build_lbvh(const DScene& S, const int* d_codes, int n, float extra_abs, cuda
     const int T = 256;
     const int nblk = (n + T - 1) / T;
     int hb[7];
+    float pad_scale = 0.f;
+    struct Group { int start, n, root_ref; float box[6]; };
+    Group groups[8];
+    int K = 0;
+    size_t total_nodes = 0;
     {
+        if (n < 2 || ngroups > 8) return RT_OK;    // nothing to build (caller tests a single primitive directly)
+        int acc = 0;
+        for (int g = 0; g < ngroups; g++) {
+            if (group_sizes[g] > 0) { groups[K].start = acc; groups[K].n = group_sizes[g]; K++; }
+            acc += group_sizes[g];
+        }
+        const int nsuper = K - 1;
+        total_nodes = (size_t)nsuper;
+        for (int g = 0; g < K; g++) total_nodes += (size_t)(groups[g].n > 1 ? groups[g].n - 1 : 0);
         CK(cudaMalloc(&plo, sizeof(float) * 3 * (size_t)n));
         CK(cudaMalloc(&phi, sizeof(float) * 3 * (size_t)n));
         CK(cudaMalloc(&gb, sizeof(int) * 8));
@@ -331,40 +356,16 @@ int build_lbvh(const DScene& S, const int* d_codes, int n, float extra_abs, cuda
         {   // fold the camera eye into the padding scale (positive float: ordered int == bits)
             float m = ord2f(hb[6]);
             if (extra_abs > m) m = extra_abs;
+            pad_scale = m;
             int enc;
             memcpy(&enc, &m, 4);
             CK(cudaMemcpyAsync(gb + 6, &enc, sizeof(int), cudaMemcpyHostToDevice, stream));
-            CK(cudaStreamSynchronize(stream));
-        }
-        if (n < 2) {   // nothing to build: the caller tests the single primitive directly
-            cudaFree(plo); cudaFree(phi); cudaFree(gb);
-            return RT_OK;
         }
         CK(cudaMalloc(&keys0, sizeof(uint32_t) * (size_t)n));
         CK(cudaMalloc(&keys1, sizeof(uint32_t) * (size_t)n));
         CK(cudaMalloc(&vals0, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&vals1, sizeof(int) * (size_t)n));
-        k_morton<<<nblk, T, 0, stream>>>(plo, phi, n, gb, keys0, vals0);
-        (*launches)++;
-        // radix sort: 4 passes x 8 bits
-        int sblocks = (n + 4095) / 4096;
-        if (sblocks > 256) sblocks = 256;
-        if (sblocks < 1) sblocks = 1;
-        int chunk = (n + sblocks - 1) / sblocks;
-        chunk = (chunk + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
-        CK(cudaMalloc(&hist, sizeof(int) * 256 * (size_t)sblocks));
-        uint32_t *kin = keys0, *kout = keys1;
-        int *vin = vals0, *vout = vals1;
-        for (int pass = 0; pass < 4; pass++) {
-            int shift = pass * 8;
-            k_sort_hist<<<sblocks, SORT_THREADS, 0, stream>>>(kin, n, chunk, shift, sblocks, hist);
-            k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * sblocks);
-            k_sort_scatter<<<sblocks, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n, chunk, shift, sblocks, hist);
-            (*launches) += 3;
-            uint32_t* tk = kin; kin = kout; kout = tk;
-            int* tv = vin; vin = vout; vout = tv;
-        }
-        // after 4 passes the sorted data is back in keys0/vals0 (kin/vin)
+        CK(cudaMalloc(&hist, sizeof(int) * 256 * 256));
         CK(cudaMalloc(&left, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&right, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&pint, sizeof(int) * (size_t)n));
@@ -372,19 +373,85 @@ int build_lbvh(const DScene& S, const int* d_codes, int n, float extra_abs, cuda
         CK(cudaMalloc(&flags, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&ilo, sizeof(float) * 3 * (size_t)n));
         CK(cudaMalloc(&ihi, sizeof(float) * 3 * (size_t)n));
-        CK(cudaMalloc(&nodes, sizeof(BvhNode) * (size_t)(n - 1)));
+        CK(cudaMalloc(&nodes, sizeof(BvhNode) * total_nodes));
         CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
-        k_karras<<<nblk, T, 0, stream>>>(kin, n, left, right, pint, pleaf);
-        k_refit<<<nblk, T, 0, stream>>>(n, vin, plo, phi, left, right, pint, pleaf, ilo, ihi, flags);
-        k_pack_nodes<<<nblk, T, 0, stream>>>(n, vin, d_codes, plo, phi, left, right, ilo, ihi, gb, nodes);
-        (*launches) += 3;
+        k_morton<<<nblk, T, 0, stream>>>(plo, phi, n, gb, keys0, vals0);
+        (*launches)++;
+        size_t node_cursor = (size_t)nsuper;
+        for (int g = 0; g < K; g++) {
+            const int gs = groups[g].start, gn = groups[g].n;
+            if (gn == 1) {
+                groups[g].root_ref = ~h_codes[gs];
+                CK(cudaMemcpyAsync(groups[g].box, plo + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(groups[g].box + 3, phi + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
+                continue;
+            }
+            const int gblk = (gn + T - 1) / T;
+            // radix sort of this group's (key, prim index) pairs: 4 passes x 8 bits
+            int sblocks = (gn + 4095) / 4096;
+            if (sblocks > 256) sblocks = 256;
+            int chunk = (gn + sblocks - 1) / sblocks;
+            chunk = (chunk + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
+            uint32_t *kin = keys0 + gs, *kout = keys1 + gs;
+            int *vin = vals0 + gs, *vout = vals1 + gs;
+            for (int pass = 0; pass < 4; pass++) {
+                int shift = pass * 8;
+                k_sort_hist<<<sblocks, SORT_THREADS, 0, stream>>>(kin, gn, chunk, shift, sblocks, hist);
+                k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * sblocks);
+                k_sort_scatter<<<sblocks, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, gn, chunk, shift, sblocks, hist);
+                (*launches) += 3;
+                uint32_t* tk = kin; kin = kout; kout = tk;
+                int* tv = vin; vin = vout; vout = tv;
+            }
+            // after 4 passes the sorted data is back in keys0/vals0
+            k_karras<<<gblk, T, 0, stream>>>(kin, gn, left + gs, right + gs, pint + gs, pleaf + gs);
+            k_refit<<<gblk, T, 0, stream>>>(gn, vin, plo, phi, left + gs, right + gs, pint + gs, pleaf + gs,
+                                            ilo + 3 * (size_t)gs, ihi + 3 * (size_t)gs, flags + gs);
+            k_pack_nodes<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
+                                                 ihi + 3 * (size_t)gs, gb, nodes, (int)node_cursor);
+            (*launches) += 3;
+            groups[g].root_ref = (int)node_cursor;
+            CK(cudaMemcpyAsync(groups[g].box, ilo + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(groups[g].box + 3, ihi + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
+            node_cursor += (size_t)(gn - 1);
+        }
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
+        if (nsuper > 0) {
+            // super nodes: S_i = (tree_i, S_{i+1}); the last one holds the last two trees
+            const float pad = 2e-6f * fmaxf(pad_scale, 1e-30f);
+            auto padded = [&](const float* b, float* out) {
+                for (int a = 0; a < 3; a++) {
+                    out[a] = b[a] - pad - fabsf(b[a]) * 2e-7f;
+                    out[3 + a] = b[3 + a] + pad + fabsf(b[3 + a]) * 2e-7f;
+                }
+            };
+            std::vector<BvhNode> sup((size_t)nsuper);
+            float rest[6];   // union of trees i+1..K-1
+            for (int a = 0; a < 6; a++) rest[a] = groups[K - 1].box[a];
+            for (int i = nsuper - 1; i >= 0; i--) {
+                float lb[6], rb[6];
+                padded(groups[i].box, lb);
+                padded(rest, rb);
+                BvhNode nd;
+                nd.a = make_float4(lb[0], lb[1], lb[2], lb[3]);
+                nd.b = make_float4(lb[4], lb[5], rb[0], rb[1]);
+                nd.c = make_float4(rb[2], rb[3], rb[4], rb[5]);
+                nd.d = make_int4(groups[i].root_ref, i == nsuper - 1 ? groups[K - 1].root_ref : i + 1, 0, 0);
+                sup[(size_t)i] = nd;
+                for (int a = 0; a < 3; a++) {
+                    rest[a] = fminf(rest[a], groups[i].box[a]);
+                    rest[3 + a] = fmaxf(rest[3 + a], groups[i].box[3 + a]);
+                }
+            }
+            CK(cudaMemcpy(nodes, sup.data(), sizeof(BvhNode) * sup.size(), cudaMemcpyHostToDevice));
+        }
     }
     cudaFree(plo); cudaFree(phi); cudaFree(gb); cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1);
     cudaFree(hist); cudaFree(left); cudaFree(right); cudaFree(pint); cudaFree(pleaf); cudaFree(flags);
     cudaFree(ilo); cudaFree(ihi);
     *out_nodes = nodes;
+    *out_count = total_nodes;
     return RT_OK;
 fail:
     cudaFree(plo); cudaFree(phi); cudaFree(gb); cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1);

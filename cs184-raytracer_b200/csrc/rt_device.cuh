@@ -144,7 +144,7 @@ struct DScene {
     int num_all;
     int num_bvh_prims;
     int single_leaf;           // BVH with exactly one primitive: its prim code
-    int pad_;
+    int shadow_mode;           // bit 0: light-major thread mapping, bit 1: deferred-leaf traversal
 };
 
 // ---- hit bookkeeping ------------------------------------------------------------
@@ -347,7 +347,7 @@ __device__ __forceinline__ float slab(const FRay& r, float lx, float ly, float l
 // The closest-hit / any-hit query == Scene::castRay (src/scene.cpp:142-167).
 //   ANYHIT: returns true when an accepted hit with world distance <= limit exists.
 //   BRUTE : ignore the LBVH and test every primitive (debug / parity aid).
-template <bool ANYHIT, bool BRUTE, bool COUNT>
+template <bool ANYHIT, bool BRUTE, bool COUNT, bool DEFER = true>
 __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool reverse, double limit, Best& best,
                                          WorkCounters& wc) {
     best.geom = -1; best.face = -1; best.dobj = 0.0; best.wd = 0.0;
@@ -372,39 +372,85 @@ __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool rever
         return __double2float_ru(x) * 1.00001f + 1e-30f;
     };
     float tlim = ANYHIT ? flimit(limit) : INF;
+    const int DONE = (int)0x80000000;      // not a valid ref (prim codes stay below 3<<29)
     int stack[RT_STACK];
+    float tstack[ANYHIT ? 1 : RT_STACK];   // closest hit: entry distance of deferred subtrees
     int sp = 0;
-    int node = 0;
-    while (true) {
-        const BvhNode* __restrict__ nptr = S.nodes + node;
-        float4 na = __ldg(&nptr->a), nb = __ldg(&nptr->b), nc = __ldg(&nptr->c);
-        int4 nd = __ldg(&nptr->d);
-        if (COUNT) wc.nodes += 2;
-        float tl = slab(fr, na.x, na.y, na.z, na.w, nb.x, nb.y, tlim);
-        float tr = slab(fr, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, tlim);
-        int first = nd.x, second = nd.y;
-        float tf = tl, ts = tr;
-        if (tr < tl) { first = nd.y; second = nd.x; tf = tr; ts = tl; }
-        int next = -1;
-        bool have_next = false;
-        // near child
-        if (tf < INF) {
-            if (first < 0) {
-                if (test_prim<ANYHIT, COUNT>(S, ~first, o, d, reverse, limit, R, best, wc)) return true;
-                if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
-            } else { next = first; have_next = true; }
+    int cur = 0;                            // root is an internal node (>= 2 primitives)
+    auto pop = [&]() -> int {
+        while (sp) {
+            --sp;
+            if (ANYHIT || tstack[sp] <= tlim) return stack[sp];   // skip subtrees a closer hit made obsolete
         }
-        if (ts < INF && ts <= tlim) {
-            if (second < 0) {
-                if (test_prim<ANYHIT, COUNT>(S, ~second, o, d, reverse, limit, R, best, wc)) return true;
-                if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
-            } else if (have_next) {
-                if (sp < RT_STACK) stack[sp++] = second;   // depth guard: LBVH over 30-bit codes stays far below
-            } else { next = second; have_next = true; }
+        return DONE;
+    };
+    auto push = [&](int ref, float t) {
+        if (sp < RT_STACK) {               // LBVH depth <= 62 with 30-bit codes + index bits
+            stack[sp] = ref;
+            if (!ANYHIT) tstack[sp] = t;
+            sp++;
         }
-        if (have_next) { node = next; continue; }
-        if (sp == 0) break;
-        node = stack[--sp];
+    };
+    if (DEFER) {
+        // "while-while" traversal: the inner loop only walks internal nodes (cheap FP32 slab
+        // tests); leaves are deferred through the same stack so that the threads of a warp
+        // reconverge before the long exact FP64 primitive test instead of diverging into it.
+        while (true) {
+            while (cur >= 0) {
+                const BvhNode* __restrict__ nptr = S.nodes + cur;
+                float4 na = __ldg(&nptr->a), nb = __ldg(&nptr->b), nc = __ldg(&nptr->c);
+                int4 nd = __ldg(&nptr->d);
+                if (COUNT) wc.nodes += 2;
+                float tl = slab(fr, na.x, na.y, na.z, na.w, nb.x, nb.y, tlim);
+                float tr = slab(fr, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, tlim);
+                bool hl = tl < INF, hr = tr < INF;
+                if (hl && hr) {
+                    bool left_first = tl <= tr;
+                    push(left_first ? nd.y : nd.x, left_first ? tr : tl);
+                    cur = left_first ? nd.x : nd.y;
+                } else if (hl) {
+                    cur = nd.x;
+                } else if (hr) {
+                    cur = nd.y;
+                } else {
+                    cur = pop();
+                }
+            }
+            if (cur == DONE) break;
+            if (test_prim<ANYHIT, COUNT>(S, ~cur, o, d, reverse, limit, R, best, wc)) return true;
+            if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
+            cur = pop();
+            if (cur == DONE) break;
+        }
+    } else {
+        // single loop: leaves are tested as soon as they are reached (better when leaves are
+        // rare relative to node visits, e.g. shadow rays leaving a height field)
+        while (cur != DONE) {
+            const BvhNode* __restrict__ nptr = S.nodes + cur;
+            float4 na = __ldg(&nptr->a), nb = __ldg(&nptr->b), nc = __ldg(&nptr->c);
+            int4 nd = __ldg(&nptr->d);
+            if (COUNT) wc.nodes += 2;
+            float tl = slab(fr, na.x, na.y, na.z, na.w, nb.x, nb.y, tlim);
+            float tr = slab(fr, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, tlim);
+            int first = nd.x, second = nd.y;
+            float tf = tl, ts = tr;
+            if (tr < tl) { first = nd.y; second = nd.x; tf = tr; ts = tl; }
+            int next = DONE;
+            if (tf < INF) {
+                if (first < 0) {
+                    if (test_prim<ANYHIT, COUNT>(S, ~first, o, d, reverse, limit, R, best, wc)) return true;
+                    if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
+                } else next = first;
+            }
+            if (ts < INF && ts <= tlim) {
+                if (second < 0) {
+                    if (test_prim<ANYHIT, COUNT>(S, ~second, o, d, reverse, limit, R, best, wc)) return true;
+                    if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
+                } else if (next != DONE) push(second, ts);
+                else next = second;
+            }
+            cur = next != DONE ? next : pop();
+        }
     }
     return false;
 }

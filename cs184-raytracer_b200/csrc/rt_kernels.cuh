@@ -254,8 +254,13 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shadow(DScene S, HitQ h, unsigned 
     unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned nsl = (unsigned)S.num_slights;
     WorkCounters wc = {0, 0, 0};
-    if (t < ctr[CTR_HITS] * nsl) {
-        unsigned j = (unsigned)(t / nsl), li = (unsigned)(t % nsl);
+    const unsigned long long nhits = ctr[CTR_HITS];
+    if (t < nhits * nsl) {
+        // light-major mapping: a warp = 32 consecutive hits (neighbouring pixels) towards the
+        // SAME light, so its shadow rays are coherent; hit-record loads coalesce
+        unsigned li, j;
+        if (S.shadow_mode & 1) { li = (unsigned)(t / nhits); j = (unsigned)(t % nhits); }
+        else { j = (unsigned)(t / nsl); li = (unsigned)(t % nsl); }
         const DLight* l = S.slights + li;
         d3 P = mk3(h.fld(0, j), h.fld(1, j), h.fld(2, j));
         d3 N = mk3(h.fld(3, j), h.fld(4, j), h.fld(5, j));
@@ -272,7 +277,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shadow(DScene S, HitQ h, unsigned 
             double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
             int inside = (h.meta[j] >> 8) & 1;
             Best best;
-            bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc);
+            bool occluded = (S.shadow_mode & 2)
+                                ? cast_ray<true, BRUTE, COUNT, true>(S, P, L, lrev != (inside != 0), dL, best, wc)
+                                : cast_ray<true, BRUTE, COUNT, false>(S, P, L, lrev != (inside != 0), dL, best, wc);
             if (!occluded) {
                 const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
                 d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
