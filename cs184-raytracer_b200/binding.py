@@ -18,7 +18,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_DIR = PKG_DIR / "lib"
+LIB_DIR = Path(os.environ.get("RT_B200_LIB_DIR", PKG_DIR / "lib"))   # override: A/B builds during development
 
 RT_OK = 0
 RT_GEOM_SPHERE, RT_GEOM_TRI, RT_GEOM_MESH = 0, 1, 2

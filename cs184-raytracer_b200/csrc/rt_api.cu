@@ -5,6 +5,7 @@
 // every batch runs the wavefront loop  trace -> shade -> shadow  once per bounce level.
 // Every level owns a ray queue of `cap` slots and a batch never exceeds cap/2 rays, so the
 // <= 2 children per hit (src/scene.cpp:127,134) can never overflow the next level.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -120,7 +121,8 @@ struct rt_context {
     DevBuf<DLight> slights, alights;
     DevBuf<double2> face_pts, face_nrm;
     DevBuf<int> flat, all_prims, bvh_prims;
-    BvhNode* nodes = nullptr;
+    DevBuf<BvhNode> nodes;
+    DeviceArena scratch;                    // upload / LBVH-build temporaries
     // render state
     size_t cap = 0;                         // ray-queue capacity per level
     std::vector<DevBuf<double>> qf;         // per level: 9*cap doubles
@@ -183,7 +185,6 @@ int rt_create(int device, rt_context** out) {
 void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->nodes) cudaFree(ctx->nodes);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -367,25 +368,30 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     if (!flat_codes.empty()) CU(cudaMemcpyAsync(ctx->flat.p, flat_codes.data(), sizeof(int) * flat_codes.size(), cudaMemcpyHostToDevice, st));
     if (!all_codes.empty()) CU(cudaMemcpyAsync(ctx->all_prims.p, all_codes.data(), sizeof(int) * all_codes.size(), cudaMemcpyHostToDevice, st));
     if (!bvh_codes.empty()) CU(cudaMemcpyAsync(ctx->bvh_prims.p, bvh_codes.data(), sizeof(int) * bvh_codes.size(), cudaMemcpyHostToDevice, st));
-    if (s->num_faces) {
-        DevBuf<double> raw_p, raw_n;
-        DevBuf<int> fg, fl;
+    {   // one arena reservation covers the raw-face staging and (afterwards, reused) the LBVH build
         const size_t nf = (size_t)s->num_faces;
-        CU(raw_p.ensure(nf * 9));
-        CU(raw_n.ensure(nf * 9));
-        CU(fg.ensure(nf));
-        CU(fl.ensure(nf));
-        CU(cudaMemcpyAsync(raw_p.p, s->face_points, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(raw_n.p, s->face_normals, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(fg.p, face_geom.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(fl.p, face_local.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
-        k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p.p, raw_n.p, fg.p, fl.p,
+        size_t need_faces = 2 * DeviceArena::padded(72 * nf) + 2 * DeviceArena::padded(4 * nf) + 4096;
+        size_t need_build = lbvh_scratch_bytes(bvh_codes.size());
+        CU(ctx->scratch.reserve(std::max(need_faces, need_build)));
+    }
+    if (s->num_faces) {
+        const size_t nf = (size_t)s->num_faces;
+        double* raw_p = ctx->scratch.take<double>(nf * 9);
+        double* raw_n = ctx->scratch.take<double>(nf * 9);
+        int* fg = ctx->scratch.take<int>(nf);
+        int* fl = ctx->scratch.take<int>(nf);
+        if (!raw_p || !raw_n || !fg || !fl) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
+        CU(cudaMemcpyAsync(raw_p, s->face_points, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(raw_n, s->face_normals, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(fg, face_geom.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(fl, face_local.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
+        k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p, raw_n, fg, fl,
                                                                   ctx->face_pts.p, ctx->face_nrm.p);
         launches++;
         LAUNCHED("k_pack_faces", st);
-        CU(cudaStreamSynchronize(st));
     }
     CU(cudaStreamSynchronize(st));
+    ctx->scratch.reset();
 
     DScene& S = ctx->S;
     memset(&S, 0, sizeof(S));
@@ -409,7 +415,6 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     CU(cudaEventRecord(ctx->ev1, st));
 
     // ---- LBVH ----
-    if (ctx->nodes) { cudaFree(ctx->nodes); ctx->nodes = nullptr; }
     cudaEvent_t evb;
     CU(cudaEventCreate(&evb));
     size_t node_count = 0;
@@ -417,11 +422,13 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
         float eye_abs = 0.f;
         for (int k = 0; k < 3; k++) eye_abs = fmaxf(eye_abs, (float)fabs(s->camera.eye[k]));
         char err[256] = "";
+        CU(ctx->nodes.ensure(bvh_codes.size() + 2));
         int brc = build_lbvh(S, ctx->bvh_prims.p, bvh_codes.data(), (int)bvh_codes.size(), group_sizes, 2, eye_abs, st,
-                             &ctx->nodes, &node_count, &launches, err, sizeof(err));
+                             ctx->scratch, ctx->nodes.p, &node_count, &launches, err, sizeof(err));
+        ctx->scratch.reset();
         if (brc != RT_OK) { cudaEventDestroy(evb); return fail(brc, "LBVH build: %s", err); }
     }
-    S.nodes = ctx->nodes;
+    S.nodes = node_count ? ctx->nodes.p : nullptr;
     cudaEventRecord(evb, st);
     CU(cudaStreamSynchronize(st));
     float ms0 = 0, ms1 = 0;

@@ -303,6 +303,15 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __r
     nodes[node_offset + i] = nd;
 }
 
+#define TAKE(var, type, count)                                                         \
+    do {                                                                               \
+        var = arena.take<type>((size_t)(count));                                       \
+        if (!var) {                                                                    \
+            snprintf(err, errlen, "LBVH scratch arena exhausted at %s", #var);         \
+            goto fail;                                                                 \
+        }                                                                              \
+    } while (0)
+
 #define CK(x)                                                                          \
     do {                                                                               \
         cudaError_t e_ = (x);                                                          \
@@ -316,15 +325,13 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __r
 // chain of super nodes: floating spheres mixed into a height-field's Morton order would
 // otherwise stretch the leaf-level boxes of the mesh over the whole air space.
 int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, const int* group_sizes, int ngroups,
-               float extra_abs, cudaStream_t stream, BvhNode** out_nodes, size_t* out_count, int* launches,
-               char* err, int errlen) {
-    *out_nodes = nullptr;
+               float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes, size_t* out_count,
+               int* launches, char* err, int errlen) {
     *out_count = 0;
     float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
     int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
     int *left = nullptr, *right = nullptr, *pint = nullptr, *pleaf = nullptr, *flags = nullptr;
     uint32_t *keys0 = nullptr, *keys1 = nullptr;
-    BvhNode* nodes = nullptr;
     const int T = 256;
     const int nblk = (n + T - 1) / T;
     int hb[7];
@@ -343,9 +350,9 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
         const int nsuper = K - 1;
         total_nodes = (size_t)nsuper;
         for (int g = 0; g < K; g++) total_nodes += (size_t)(groups[g].n > 1 ? groups[g].n - 1 : 0);
-        CK(cudaMalloc(&plo, sizeof(float) * 3 * (size_t)n));
-        CK(cudaMalloc(&phi, sizeof(float) * 3 * (size_t)n));
-        CK(cudaMalloc(&gb, sizeof(int) * 8));
+        TAKE(plo, float, 3 * (size_t)n);
+        TAKE(phi, float, 3 * (size_t)n);
+        TAKE(gb, int, 8);
         int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000,
                        (int)0x80000000, 0};
         CK(cudaMemcpyAsync(gb, init, sizeof(init), cudaMemcpyHostToDevice, stream));
@@ -361,19 +368,18 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
             memcpy(&enc, &m, 4);
             CK(cudaMemcpyAsync(gb + 6, &enc, sizeof(int), cudaMemcpyHostToDevice, stream));
         }
-        CK(cudaMalloc(&keys0, sizeof(uint32_t) * (size_t)n));
-        CK(cudaMalloc(&keys1, sizeof(uint32_t) * (size_t)n));
-        CK(cudaMalloc(&vals0, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&vals1, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&hist, sizeof(int) * 256 * 256));
-        CK(cudaMalloc(&left, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&right, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&pint, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&pleaf, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&flags, sizeof(int) * (size_t)n));
-        CK(cudaMalloc(&ilo, sizeof(float) * 3 * (size_t)n));
-        CK(cudaMalloc(&ihi, sizeof(float) * 3 * (size_t)n));
-        CK(cudaMalloc(&nodes, sizeof(BvhNode) * total_nodes));
+        TAKE(keys0, uint32_t, (size_t)n);
+        TAKE(keys1, uint32_t, (size_t)n);
+        TAKE(vals0, int, (size_t)n);
+        TAKE(vals1, int, (size_t)n);
+        TAKE(hist, int, 256 * 256);
+        TAKE(left, int, (size_t)n);
+        TAKE(right, int, (size_t)n);
+        TAKE(pint, int, (size_t)n);
+        TAKE(pleaf, int, (size_t)n);
+        TAKE(flags, int, (size_t)n);
+        TAKE(ilo, float, 3 * (size_t)n);
+        TAKE(ihi, float, 3 * (size_t)n);
         CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
         k_morton<<<nblk, T, 0, stream>>>(plo, phi, n, gb, keys0, vals0);
         (*launches)++;
@@ -447,16 +453,9 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
             CK(cudaMemcpy(nodes, sup.data(), sizeof(BvhNode) * sup.size(), cudaMemcpyHostToDevice));
         }
     }
-    cudaFree(plo); cudaFree(phi); cudaFree(gb); cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1);
-    cudaFree(hist); cudaFree(left); cudaFree(right); cudaFree(pint); cudaFree(pleaf); cudaFree(flags);
-    cudaFree(ilo); cudaFree(ihi);
-    *out_nodes = nodes;
     *out_count = total_nodes;
     return RT_OK;
 fail:
-    cudaFree(plo); cudaFree(phi); cudaFree(gb); cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1);
-    cudaFree(hist); cudaFree(left); cudaFree(right); cudaFree(pint); cudaFree(pleaf); cudaFree(flags);
-    cudaFree(ilo); cudaFree(ihi); cudaFree(nodes);
     return RT_ERR_CUDA;
 }
 

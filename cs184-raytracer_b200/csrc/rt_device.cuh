@@ -312,32 +312,35 @@ __device__ __forceinline__ bool test_prim(const DScene& S, int code, d3 o, d3 d,
 
 // ---- FP32 conservative slab test -------------------------------------------------
 struct FRay {
-    float ox, oy, oz;
-    float ix, iy, iz;   // 1/d (clamped away from 0)
+    float ix, iy, iz;      // 1/d (clamped away from 0)
+    float bx, by, bz;      // -o/d, so that t = plane * (1/d) + (-o/d) is one FMA
 };
 __device__ __forceinline__ FRay make_fray(d3 o, d3 d) {
     FRay r;
-    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+    float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
     float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
     const float tiny = 1e-30f;
     if (fabsf(dx) < tiny) dx = copysignf(tiny, dx);
     if (fabsf(dy) < tiny) dy = copysignf(tiny, dy);
     if (fabsf(dz) < tiny) dz = copysignf(tiny, dz);
     r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+    r.bx = -ox * r.ix; r.by = -oy * r.iy; r.bz = -oz * r.iz;
     return r;
 }
-// Entry distance of the (already padded) box, or +inf when missed.  tmax is widened by a
-// few ulps and tmin compared against a widened limit, so FP32 rounding can only let MORE
-// boxes through, never fewer.
+// Entry distance of the (already padded) box, or +inf when missed.  The FMA form has a
+// positional error of a few ulp(|o|) per axis, which the box padding (2e-6 x the largest
+// scene coordinate, rt_bvh.cu) covers; tmax is widened and tmin narrowed by a few ulps and
+// tmin is compared against a widened limit, so FP32 rounding can only let MORE boxes
+// through, never fewer.  (Explicit __fmaf_rn: this file is compiled with -fmad=false.)
 __device__ __forceinline__ float slab(const FRay& r, float lx, float ly, float lz, float hx, float hy, float hz,
                                       float tlimit) {
-    float t0x = (lx - r.ox) * r.ix, t1x = (hx - r.ox) * r.ix;
-    float t0y = (ly - r.oy) * r.iy, t1y = (hy - r.oy) * r.iy;
-    float t0z = (lz - r.oz) * r.iz, t1z = (hz - r.oz) * r.iz;
+    float t0x = __fmaf_rn(lx, r.ix, r.bx), t1x = __fmaf_rn(hx, r.ix, r.bx);
+    float t0y = __fmaf_rn(ly, r.iy, r.by), t1y = __fmaf_rn(hy, r.iy, r.by);
+    float t0z = __fmaf_rn(lz, r.iz, r.bz), t1z = __fmaf_rn(hz, r.iz, r.bz);
     float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
     float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    tmax = tmax + fabsf(tmax) * 5e-7f + 1e-30f;
-    tmin = tmin - fabsf(tmin) * 5e-7f;
+    tmax = __fmaf_rn(fabsf(tmax), 1e-6f, tmax) + 1e-30f;
+    tmin = __fmaf_rn(fabsf(tmin), -1e-6f, tmin);
     bool hit = (tmin <= tmax) && (tmax >= 0.f) && (tmin <= tlimit);
     return hit ? fmaxf(tmin, 0.f) : __int_as_float(0x7f800000);
 }

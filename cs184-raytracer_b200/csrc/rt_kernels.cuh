@@ -14,6 +14,15 @@
 namespace rt {
 
 #define RT_BLOCK 128
+// Minimum resident blocks per SM (= register cap) of the two traversal kernels.  Both are
+// latency-bound gathers: measured on B200 (synthetic 8K frame, same box) k_shadow 210 ms at
+// 116 regs/4 blocks -> 140 ms at 10 blocks, k_trace 76 ms at 148 regs/3 blocks -> 51 ms at 8.
+#ifndef RT_SHADOW_MINBLOCKS
+#define RT_SHADOW_MINBLOCKS 10
+#endif
+#ifndef RT_TRACE_MINBLOCKS
+#define RT_TRACE_MINBLOCKS 8
+#endif
 
 // Ray queue, SoA over `cap` slots.
 struct RayQ {
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long
 // Closest hit for every queued ray; hits are appended (compacted) to the hit queue.
 // ids_geom/ids_face (optional, indexed by framebuffer slot) receive the hit ids.
 template <bool BRUTE, bool COUNT>
-__global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RayQ q, size_t off, int n, HitQ h,
+__global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S, RayQ q, size_t off, int n, HitQ h,
                                                      unsigned long long* ctr, int* ids_geom, int* ids_face) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = off + (size_t)t;
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(DScene S, HitQ h, unsigned l
 
 // One thread per (hit, shadow light): occlusion query + Phong terms of that light.
 template <bool BRUTE, bool COUNT>
-__global__ void __launch_bounds__(RT_BLOCK) k_shadow(DScene S, HitQ h, unsigned long long* ctr, double* fb) {
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene S, HitQ h, unsigned long long* ctr, double* fb) {
     unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned nsl = (unsigned)S.num_slights;
     WorkCounters wc = {0, 0, 0};
@@ -277,9 +286,11 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shadow(DScene S, HitQ h, unsigned 
             double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
             int inside = (h.meta[j] >> 8) & 1;
             Best best;
-            bool occluded = (S.shadow_mode & 2)
-                                ? cast_ray<true, BRUTE, COUNT, true>(S, P, L, lrev != (inside != 0), dL, best, wc)
-                                : cast_ray<true, BRUTE, COUNT, false>(S, P, L, lrev != (inside != 0), dL, best, wc);
+#ifdef RT_SHADOW_IMMEDIATE
+            bool occluded = cast_ray<true, BRUTE, COUNT, false>(S, P, L, lrev != (inside != 0), dL, best, wc);
+#else
+            bool occluded = cast_ray<true, BRUTE, COUNT, true>(S, P, L, lrev != (inside != 0), dL, best, wc);
+#endif
             if (!occluded) {
                 const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
                 d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
