@@ -411,7 +411,8 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     S.num_all = (int)all_codes.size();
     S.num_bvh_prims = (int)bvh_codes.size();
     S.single_leaf = bvh_codes.size() == 1 ? bvh_codes[0] : 0;
-    S.shadow_mode = getenv("RT_SHADOW_MODE") ? atoi(getenv("RT_SHADOW_MODE")) : 3;
+    // bit 0: light-major thread mapping of k_shadow (hit-major otherwise; kept for A/B runs)
+    S.shadow_mode = getenv("RT_SHADOW_MODE") ? atoi(getenv("RT_SHADOW_MODE")) : 1;
     CU(cudaEventRecord(ctx->ev1, st));
 
     // ---- LBVH ----

@@ -5,6 +5,7 @@
 // hitsBoundingBox src/geometry.cpp:5-29).  The boxes only CULL (FP32, padded outward);
 // every hit decision is still the exact FP64 test in rt_device.cuh.
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -267,39 +268,71 @@ __global__ void k_refit(int n, const int* __restrict__ vals, const float* __rest
     }
 }
 
-__global__ void k_pack_nodes(int n, const int* __restrict__ vals, const int* __restrict__ codes,
-                             const float* __restrict__ plo, const float* __restrict__ phi,
-                             const int* __restrict__ left, const int* __restrict__ right,
-                             const float* __restrict__ ilo, const float* __restrict__ ihi,
-                             const int* __restrict__ gbounds, BvhNode* __restrict__ nodes, int node_offset) {
+// depth of every internal node of one tree (root = 0) by walking the parent chain
+__global__ void k_depth(int n, const int* __restrict__ parent_int, int* __restrict__ depth) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
+    int d = 0;
+    for (int p = parent_int[i]; p >= 0; p = parent_int[p]) d++;
+    depth[i] = d;
+}
+
+// Binary Karras nodes at EVEN depth become 4-wide nodes: each internal child (odd depth) is
+// replaced by its own two children.  Wide nodes keep the binary node's index (+ offset), so
+// no compaction pass is needed; odd-depth slots of the array stay unused.
+__global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __restrict__ codes,
+                            const float* __restrict__ plo, const float* __restrict__ phi,
+                            const int* __restrict__ left, const int* __restrict__ right,
+                            const float* __restrict__ ilo, const float* __restrict__ ihi,
+                            const int* __restrict__ depth, const int* __restrict__ gbounds,
+                            BvhNode* __restrict__ nodes, int node_offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (depth[i] & 1) return;
     // pad: a few FP32 ulps at the scene's largest coordinate (covers the slab test's rounding)
     const float pad = 2e-6f * fmaxf(ord2f(gbounds[6]), 1e-30f);
-    float bx[2][6];
-    int ref[2];
+    int slots[4];
+    int ns = 0;
     int ch[2] = {left[i], right[i]};
     for (int k = 0; k < 2; k++) {
+        if (ch[k] < 0) slots[ns++] = ch[k];
+        else { slots[ns++] = left[ch[k]]; slots[ns++] = right[ch[k]]; }
+    }
+    float lo[3][4], hi[3][4];
+    int ref[4];
+    // empty slots get NaN boxes: every comparison of the slab test is false, so they never
+    // hit (an "inverted" box would: min/max make the slab test symmetric in lo/hi)
+    const float QNAN = __int_as_float(0x7fc00000);
+    for (int k = 0; k < 4; k++) {
+        if (k >= ns) {
+            for (int a = 0; a < 3; a++) { lo[a][k] = QNAN; hi[a][k] = QNAN; }
+            ref[k] = BVH_DONE;
+            continue;
+        }
         const float *bl, *bh;
-        if (ch[k] < 0) {
-            int p = vals[~ch[k]];
+        if (slots[k] < 0) {
+            int p = vals[~slots[k]];
             bl = plo + 3 * (size_t)p; bh = phi + 3 * (size_t)p;
             ref[k] = ~codes[p];
         } else {
-            bl = ilo + 3 * (size_t)ch[k]; bh = ihi + 3 * (size_t)ch[k];
-            ref[k] = ch[k] + node_offset;
+            bl = ilo + 3 * (size_t)slots[k]; bh = ihi + 3 * (size_t)slots[k];
+            ref[k] = slots[k] + node_offset;
         }
         for (int a = 0; a < 3; a++) {
             float l = bl[a], h = bh[a];
-            bx[k][a] = l - pad - fabsf(l) * 2e-7f;
-            bx[k][3 + a] = h + pad + fabsf(h) * 2e-7f;
+            lo[a][k] = l - pad - fabsf(l) * 2e-7f;
+            hi[a][k] = h + pad + fabsf(h) * 2e-7f;
         }
     }
     BvhNode nd;
-    nd.a = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
-    nd.b = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
-    nd.c = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
-    nd.d = make_int4(ref[0], ref[1], 0, 0);
+    nd.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
+    nd.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+    nd.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+    nd.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+    nd.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+    nd.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+    nd.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    nd.pad_ = make_int4(0, 0, 0, 0);
     nodes[node_offset + i] = nd;
 }
 
@@ -330,24 +363,24 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
     *out_count = 0;
     float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
     int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
-    int *left = nullptr, *right = nullptr, *pint = nullptr, *pleaf = nullptr, *flags = nullptr;
+    int *left = nullptr, *right = nullptr, *pint = nullptr, *pleaf = nullptr, *flags = nullptr, *depth = nullptr;
     uint32_t *keys0 = nullptr, *keys1 = nullptr;
     const int T = 256;
     const int nblk = (n + T - 1) / T;
     int hb[7];
     float pad_scale = 0.f;
     struct Group { int start, n, root_ref; float box[6]; };
-    Group groups[8];
+    Group groups[4];
     int K = 0;
     size_t total_nodes = 0;
     {
-        if (n < 2 || ngroups > 8) return RT_OK;    // nothing to build (caller tests a single primitive directly)
+        if (n < 2 || ngroups > 4) return RT_OK;    // nothing to build (caller tests a single primitive directly)
         int acc = 0;
         for (int g = 0; g < ngroups; g++) {
             if (group_sizes[g] > 0) { groups[K].start = acc; groups[K].n = group_sizes[g]; K++; }
             acc += group_sizes[g];
         }
-        const int nsuper = K - 1;
+        const int nsuper = K > 1 ? 1 : 0;      // one 4-wide super node joins up to four trees
         total_nodes = (size_t)nsuper;
         for (int g = 0; g < K; g++) total_nodes += (size_t)(groups[g].n > 1 ? groups[g].n - 1 : 0);
         TAKE(plo, float, 3 * (size_t)n);
@@ -378,6 +411,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
         TAKE(pint, int, (size_t)n);
         TAKE(pleaf, int, (size_t)n);
         TAKE(flags, int, (size_t)n);
+        TAKE(depth, int, (size_t)n);
         TAKE(ilo, float, 3 * (size_t)n);
         TAKE(ihi, float, 3 * (size_t)n);
         CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
@@ -413,9 +447,10 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
             k_karras<<<gblk, T, 0, stream>>>(kin, gn, left + gs, right + gs, pint + gs, pleaf + gs);
             k_refit<<<gblk, T, 0, stream>>>(gn, vin, plo, phi, left + gs, right + gs, pint + gs, pleaf + gs,
                                             ilo + 3 * (size_t)gs, ihi + 3 * (size_t)gs, flags + gs);
-            k_pack_nodes<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
-                                                 ihi + 3 * (size_t)gs, gb, nodes, (int)node_cursor);
-            (*launches) += 3;
+            k_depth<<<gblk, T, 0, stream>>>(gn, pint + gs, depth + gs);
+            k_pack_wide<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
+                                                ihi + 3 * (size_t)gs, depth + gs, gb, nodes, (int)node_cursor);
+            (*launches) += 4;
             groups[g].root_ref = (int)node_cursor;
             CK(cudaMemcpyAsync(groups[g].box, ilo + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
             CK(cudaMemcpyAsync(groups[g].box + 3, ihi + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
@@ -424,33 +459,31 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
         if (nsuper > 0) {
-            // super nodes: S_i = (tree_i, S_{i+1}); the last one holds the last two trees
             const float pad = 2e-6f * fmaxf(pad_scale, 1e-30f);
-            auto padded = [&](const float* b, float* out) {
+            const float QNAN = NAN;         // empty slots: never hit (see k_pack_wide)
+            float lo[3][4], hi[3][4];
+            int ref[4];
+            for (int k = 0; k < 4; k++) {
+                for (int a = 0; a < 3; a++) { lo[a][k] = QNAN; hi[a][k] = QNAN; }
+                ref[k] = BVH_DONE;
+                if (k >= K) continue;
+                ref[k] = groups[k].root_ref;
                 for (int a = 0; a < 3; a++) {
-                    out[a] = b[a] - pad - fabsf(b[a]) * 2e-7f;
-                    out[3 + a] = b[3 + a] + pad + fabsf(b[3 + a]) * 2e-7f;
-                }
-            };
-            std::vector<BvhNode> sup((size_t)nsuper);
-            float rest[6];   // union of trees i+1..K-1
-            for (int a = 0; a < 6; a++) rest[a] = groups[K - 1].box[a];
-            for (int i = nsuper - 1; i >= 0; i--) {
-                float lb[6], rb[6];
-                padded(groups[i].box, lb);
-                padded(rest, rb);
-                BvhNode nd;
-                nd.a = make_float4(lb[0], lb[1], lb[2], lb[3]);
-                nd.b = make_float4(lb[4], lb[5], rb[0], rb[1]);
-                nd.c = make_float4(rb[2], rb[3], rb[4], rb[5]);
-                nd.d = make_int4(groups[i].root_ref, i == nsuper - 1 ? groups[K - 1].root_ref : i + 1, 0, 0);
-                sup[(size_t)i] = nd;
-                for (int a = 0; a < 3; a++) {
-                    rest[a] = fminf(rest[a], groups[i].box[a]);
-                    rest[3 + a] = fmaxf(rest[3 + a], groups[i].box[3 + a]);
+                    float l = groups[k].box[a], h = groups[k].box[3 + a];
+                    lo[a][k] = l - pad - fabsf(l) * 2e-7f;
+                    hi[a][k] = h + pad + fabsf(h) * 2e-7f;
                 }
             }
-            CK(cudaMemcpy(nodes, sup.data(), sizeof(BvhNode) * sup.size(), cudaMemcpyHostToDevice));
+            BvhNode nd;
+            nd.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
+            nd.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+            nd.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+            nd.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+            nd.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+            nd.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+            nd.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
+            nd.pad_ = make_int4(0, 0, 0, 0);
+            CK(cudaMemcpy(nodes, &nd, sizeof(BvhNode), cudaMemcpyHostToDevice));
         }
     }
     *out_count = total_nodes;

@@ -110,14 +110,18 @@ struct DCamera {
 // Normals: n0.xy | n0.z n1.x | n1.yz | n2.xy | n2.z pad.
 #define RT_FACE_D2 5
 
-// LBVH node pair, 64 B: both children's FP32 boxes + two child references.
-// ref >= 0: internal node index; ref < 0: leaf, prim code = ~ref.
+// 4-wide LBVH node, 128 B = 8 x float4: the four child boxes as SoA (FP32, padded outward)
+// + four child references.  ref >= 0: wide-node index; ref < 0: leaf, prim code = ~ref;
+// empty slot: ref = BVH_DONE with a NaN box (never hit).  A wide node is a binary
+// Karras node at even depth with its grandchildren pulled up, which halves the number of
+// dependent fetches per ray (the traversal kernels are latency-bound).
 struct alignas(16) BvhNode {
-    float4 a;   // L.lo.xyz, L.hi.x
-    float4 b;   // L.hi.yz,  R.lo.xy
-    float4 c;   // R.lo.z,   R.hi.xyz
-    int4 d;     // left ref, right ref, unused, unused
+    float4 lox, loy, loz;
+    float4 hix, hiy, hiz;
+    int4 ref;
+    int4 pad_;
 };
+#define BVH_DONE ((int)0x80000000)     // not a valid ref (prim codes stay below 3<<29)
 
 // prim code: kind in the top 2 bits of a 31-bit value
 #define PRIM_KIND_SHIFT 29
@@ -144,7 +148,7 @@ struct DScene {
     int num_all;
     int num_bvh_prims;
     int single_leaf;           // BVH with exactly one primitive: its prim code
-    int shadow_mode;           // bit 0: light-major thread mapping, bit 1: deferred-leaf traversal
+    int shadow_mode;           // bit 0: light-major thread mapping of k_shadow
 };
 
 // ---- hit bookkeeping ------------------------------------------------------------
@@ -345,12 +349,102 @@ __device__ __forceinline__ float slab(const FRay& r, float lx, float ly, float l
     return hit ? fmaxf(tmin, 0.f) : __int_as_float(0x7f800000);
 }
 
-#define RT_STACK 64
+#define RT_STACK 96
+#ifndef RT_ANYHIT_UNSORTED
+#define RT_ANYHIT_UNSORTED 1
+#endif
+
+__device__ __forceinline__ float prune_limit(double x) {
+    // FP32 prune limit, rounded up with slack
+    if (!(x < 3.0e38)) return __int_as_float(0x7f800000);
+    return __double2float_ru(x) * 1.00001f + 1e-30f;
+}
+
+// Traversal state of one ray over the 4-wide LBVH.  Leaves are deferred through the same
+// stack as internal nodes ("while-while"): descend() only walks internal nodes (cheap FP32
+// slab tests) and returns at a leaf, so the threads of a warp reconverge before the long
+// exact FP64 primitive test instead of diverging into it.
+template <bool ANYHIT>
+struct Trav {
+    int stack[RT_STACK];
+    float tstack[ANYHIT ? 1 : RT_STACK];   // closest hit: entry distance of deferred subtrees
+    int sp;
+    int cur;
+
+    __device__ __forceinline__ void start() { sp = 0; cur = 0; }   // node 0 is the root
+    __device__ __forceinline__ int pop(float tlim) {
+        while (sp) {
+            --sp;
+            if (ANYHIT || tstack[sp] <= tlim) return stack[sp];   // skip subtrees a closer hit made obsolete
+        }
+        return BVH_DONE;
+    }
+    __device__ __forceinline__ void push(int ref, float t) {
+        if (sp < RT_STACK) {               // 3 pushes per wide level, depth <= 31 wide levels
+            stack[sp] = ref;
+            if (!ANYHIT) tstack[sp] = t;
+            sp++;
+        }
+    }
+    // Walk internal nodes until `cur` is a leaf reference (< 0) or BVH_DONE.
+    template <bool COUNT>
+    __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float tlim, WorkCounters& wc) {
+        while (cur >= 0) {
+            const float4* __restrict__ np = reinterpret_cast<const float4*>(S.nodes + cur);
+            const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
+            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+            const int4 ref = __ldg(reinterpret_cast<const int4*>(np + 6));
+            if (COUNT) wc.nodes += 4;
+            const float t0 = slab(fr, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tlim);
+            const float t1 = slab(fr, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tlim);
+            const float t2 = slab(fr, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tlim);
+            const float t3 = slab(fr, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tlim);
+            if (ANYHIT && RT_ANYHIT_UNSORTED) {
+                // occlusion query: any order will do; take the first hit slot, defer the others
+                const float INF = __int_as_float(0x7f800000);
+                int next = BVH_DONE;
+                if (t3 < INF) next = ref.w;
+                if (t2 < INF) { if (next != BVH_DONE) push(next, 0.f); next = ref.z; }
+                if (t1 < INF) { if (next != BVH_DONE) push(next, 0.f); next = ref.y; }
+                if (t0 < INF) { if (next != BVH_DONE) push(next, 0.f); next = ref.x; }
+                cur = next != BVH_DONE ? next : pop(tlim);
+                continue;
+            }
+            // sort the four (distance, slot) pairs: slot index rides in the two low mantissa
+            // bits (t >= 0, so the float bit patterns order like unsigned ints; +inf = miss)
+            unsigned k0 = (__float_as_uint(t0) & ~3u) | 0u, k1 = (__float_as_uint(t1) & ~3u) | 1u;
+            unsigned k2 = (__float_as_uint(t2) & ~3u) | 2u, k3 = (__float_as_uint(t3) & ~3u) | 3u;
+            unsigned a, b;
+            a = min(k0, k1); b = max(k0, k1); k0 = a; k1 = b;
+            a = min(k2, k3); b = max(k2, k3); k2 = a; k3 = b;
+            a = min(k0, k2); b = max(k0, k2); k0 = a; k2 = b;
+            a = min(k1, k3); b = max(k1, k3); k1 = a; k3 = b;
+            a = min(k1, k2); b = max(k1, k2); k1 = a; k2 = b;
+            const unsigned MISS = 0x7f800000u;
+            auto ref_of = [&](unsigned k) -> int {
+                unsigned i = k & 3u;
+                return i == 0 ? ref.x : (i == 1 ? ref.y : (i == 2 ? ref.z : ref.w));
+            };
+            if (k0 < MISS) {
+                if (k1 < MISS) {
+                    if (k2 < MISS) {
+                        if (k3 < MISS) push(ref_of(k3), __uint_as_float(k3 & ~3u));
+                        push(ref_of(k2), __uint_as_float(k2 & ~3u));
+                    }
+                    push(ref_of(k1), __uint_as_float(k1 & ~3u));
+                }
+                cur = ref_of(k0);
+            } else {
+                cur = pop(tlim);
+            }
+        }
+    }
+};
 
 // The closest-hit / any-hit query == Scene::castRay (src/scene.cpp:142-167).
 //   ANYHIT: returns true when an accepted hit with world distance <= limit exists.
 //   BRUTE : ignore the LBVH and test every primitive (debug / parity aid).
-template <bool ANYHIT, bool BRUTE, bool COUNT, bool DEFER = true>
+template <bool ANYHIT, bool BRUTE, bool COUNT>
 __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool reverse, double limit, Best& best,
                                          WorkCounters& wc) {
     best.geom = -1; best.face = -1; best.dobj = 0.0; best.wd = 0.0;
@@ -368,92 +462,16 @@ __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool rever
         return test_prim<ANYHIT, COUNT>(S, S.single_leaf, o, d, reverse, limit, R, best, wc);
 
     const FRay fr = make_fray(o, d);
-    const float INF = __int_as_float(0x7f800000);
-    // prune limit in FP32, rounded up with slack; shrinks as closer hits are found
-    auto flimit = [&](double x) -> float {
-        if (!(x < 3.0e38)) return INF;
-        return __double2float_ru(x) * 1.00001f + 1e-30f;
-    };
-    float tlim = ANYHIT ? flimit(limit) : INF;
-    const int DONE = (int)0x80000000;      // not a valid ref (prim codes stay below 3<<29)
-    int stack[RT_STACK];
-    float tstack[ANYHIT ? 1 : RT_STACK];   // closest hit: entry distance of deferred subtrees
-    int sp = 0;
-    int cur = 0;                            // root is an internal node (>= 2 primitives)
-    auto pop = [&]() -> int {
-        while (sp) {
-            --sp;
-            if (ANYHIT || tstack[sp] <= tlim) return stack[sp];   // skip subtrees a closer hit made obsolete
-        }
-        return DONE;
-    };
-    auto push = [&](int ref, float t) {
-        if (sp < RT_STACK) {               // LBVH depth <= 62 with 30-bit codes + index bits
-            stack[sp] = ref;
-            if (!ANYHIT) tstack[sp] = t;
-            sp++;
-        }
-    };
-    if (DEFER) {
-        // "while-while" traversal: the inner loop only walks internal nodes (cheap FP32 slab
-        // tests); leaves are deferred through the same stack so that the threads of a warp
-        // reconverge before the long exact FP64 primitive test instead of diverging into it.
-        while (true) {
-            while (cur >= 0) {
-                const BvhNode* __restrict__ nptr = S.nodes + cur;
-                float4 na = __ldg(&nptr->a), nb = __ldg(&nptr->b), nc = __ldg(&nptr->c);
-                int4 nd = __ldg(&nptr->d);
-                if (COUNT) wc.nodes += 2;
-                float tl = slab(fr, na.x, na.y, na.z, na.w, nb.x, nb.y, tlim);
-                float tr = slab(fr, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, tlim);
-                bool hl = tl < INF, hr = tr < INF;
-                if (hl && hr) {
-                    bool left_first = tl <= tr;
-                    push(left_first ? nd.y : nd.x, left_first ? tr : tl);
-                    cur = left_first ? nd.x : nd.y;
-                } else if (hl) {
-                    cur = nd.x;
-                } else if (hr) {
-                    cur = nd.y;
-                } else {
-                    cur = pop();
-                }
-            }
-            if (cur == DONE) break;
-            if (test_prim<ANYHIT, COUNT>(S, ~cur, o, d, reverse, limit, R, best, wc)) return true;
-            if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
-            cur = pop();
-            if (cur == DONE) break;
-        }
-    } else {
-        // single loop: leaves are tested as soon as they are reached (better when leaves are
-        // rare relative to node visits, e.g. shadow rays leaving a height field)
-        while (cur != DONE) {
-            const BvhNode* __restrict__ nptr = S.nodes + cur;
-            float4 na = __ldg(&nptr->a), nb = __ldg(&nptr->b), nc = __ldg(&nptr->c);
-            int4 nd = __ldg(&nptr->d);
-            if (COUNT) wc.nodes += 2;
-            float tl = slab(fr, na.x, na.y, na.z, na.w, nb.x, nb.y, tlim);
-            float tr = slab(fr, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, tlim);
-            int first = nd.x, second = nd.y;
-            float tf = tl, ts = tr;
-            if (tr < tl) { first = nd.y; second = nd.x; tf = tr; ts = tl; }
-            int next = DONE;
-            if (tf < INF) {
-                if (first < 0) {
-                    if (test_prim<ANYHIT, COUNT>(S, ~first, o, d, reverse, limit, R, best, wc)) return true;
-                    if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
-                } else next = first;
-            }
-            if (ts < INF && ts <= tlim) {
-                if (second < 0) {
-                    if (test_prim<ANYHIT, COUNT>(S, ~second, o, d, reverse, limit, R, best, wc)) return true;
-                    if (!ANYHIT && best.geom >= 0) tlim = flimit(best.wd);
-                } else if (next != DONE) push(second, ts);
-                else next = second;
-            }
-            cur = next != DONE ? next : pop();
-        }
+    float tlim = ANYHIT ? prune_limit(limit) : __int_as_float(0x7f800000);   // shrinks as closer hits are found
+    Trav<ANYHIT> T;
+    T.start();
+    while (true) {
+        T.template descend<COUNT>(S, fr, tlim, wc);
+        if (T.cur == BVH_DONE) break;
+        if (test_prim<ANYHIT, COUNT>(S, ~T.cur, o, d, reverse, limit, R, best, wc)) return true;
+        if (!ANYHIT && best.geom >= 0) tlim = prune_limit(best.wd);
+        T.cur = T.pop(tlim);
+        if (T.cur == BVH_DONE) break;
     }
     return false;
 }

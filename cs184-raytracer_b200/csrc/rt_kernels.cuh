@@ -286,11 +286,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
             double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
             int inside = (h.meta[j] >> 8) & 1;
             Best best;
-#ifdef RT_SHADOW_IMMEDIATE
-            bool occluded = cast_ray<true, BRUTE, COUNT, false>(S, P, L, lrev != (inside != 0), dL, best, wc);
-#else
-            bool occluded = cast_ray<true, BRUTE, COUNT, true>(S, P, L, lrev != (inside != 0), dL, best, wc);
-#endif
+            bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc);
             if (!occluded) {
                 const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
                 d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));

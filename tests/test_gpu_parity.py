@@ -190,3 +190,37 @@ def test_tile_sharding_emulated_on_one_gpu(pkg, gpu_renderer, scenes):
         gpu_renderer.unpack_tiles(p0, packed.data_ptr(), frame.data_ptr(), rgb8=True)
         torch.cuda.synchronize()
         assert np.array_equal(frame.cpu().numpy(), full)
+
+
+def test_as2_cli_renders_the_golden(pkg, tmp_path):
+    """The drop-in executable end to end: same command line as notes/notes-08.txt (smaller
+    thread count is irrelevant: -t is accepted and ignored), PNG within the north_star gate."""
+    import subprocess
+    from conftest import PKG_DIR
+    out = tmp_path / "image-08.png"
+    proc = subprocess.run([str(PKG_DIR / "bin" / "as2"), str(scene_path("inputs/input-08.rti")), "-o", str(out),
+                           "-h", "1000", "-w", "1000", "-t", "8"], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    assert "Rendering scene (1000000/1000000) (100.0%) ..." in proc.stdout
+    img = decode_png(out)
+    gold = decode_png(GOLDEN / "outputs" / "image-08.png")
+    diff = np.abs(img.astype(np.int16) - gold.astype(np.int16)).max(axis=2)
+    assert float((diff <= 1).mean()) >= 0.999 and int(diff.max()) <= 4
+
+
+def test_progress_callback_contract(pkg, gpu_renderer, scenes):
+    """Monotone, on the calling thread, and a final (total, total) call (src/scene.cpp:41-47)."""
+    import ctypes as C
+    import threading
+    gpu_renderer.upload(scenes("input-05"))
+    calls = []
+    main_thread = threading.get_ident()
+    CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_void_p)
+    cb = CB(lambda done, total, user: calls.append((done, total, threading.get_ident())))
+    p = pkg.make_params(640, 480, 3)
+    out = np.empty((480, 640, 3))
+    rc = gpu_renderer.lib.rt_render(gpu_renderer._h, C.byref(p), out.ctypes.data_as(C.c_void_p), cb, None)
+    assert rc == 0 and calls
+    assert calls[-1][:2] == (640 * 480, 640 * 480)
+    assert all(a[0] <= b[0] for a, b in zip(calls, calls[1:]))
+    assert all(c[2] == main_thread for c in calls)
