@@ -86,7 +86,7 @@ RT_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_scene_upload", "rt_render", "rt_render_rgb8",
     "rt_render_device", "rt_render_device_rgb8", "rt_tile_count", "rt_tile_count_total", "rt_tile_count_max",
     "rt_unpack_tiles_rgb8", "rt_unpack_tiles", "rt_primary_ids", "rt_cast_rays", "rt_get_stats",
-    "rt_microbench_gather", "rt_scene_device_bytes",
+    "rt_microbench_gather", "rt_scene_device_bytes", "rt_intersection_max", "rt_divide_device",
 ]
 
 _rt = None
@@ -127,6 +127,8 @@ def load_rt() -> C.CDLL:
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(rt_stats)]
         lib.rt_microbench_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+        lib.rt_intersection_max.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        lib.rt_divide_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
         lib.rt_scene_device_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _rt = lib
     return _rt
@@ -303,6 +305,15 @@ class Renderer:
         self._check(self.lib.rt_cast_rays(self._h, n, _ptr(org), _ptr(direction), _ptr(rev), flags, _ptr(geom), _ptr(face),
                                           _ptr(dist), _ptr(point), _ptr(normal)), "rt_cast_rays")
         return geom, face, dist, point, normal
+
+    def intersection_max(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.rt_intersection_max(self._h, C.byref(v)), "rt_intersection_max")
+        return float(v.value)
+
+    def divide_device(self, d_ptr: int, count: int, divisor: float, stream: int = 0):
+        self._check(self.lib.rt_divide_device(self._h, C.c_void_p(d_ptr), int(count), float(divisor), C.c_void_p(stream)),
+                    "rt_divide_device")
 
     def device_bytes(self):
         a, b = C.c_uint64(), C.c_uint64()

@@ -906,6 +906,30 @@ int rt_cast_rays(rt_context* ctx, int64_t n, const double* org, const double* di
     return RT_OK;
 }
 
+int rt_intersection_max(rt_context* ctx, double* out_max) {
+    if (!ctx || !out_max) return fail(RT_ERR_INVALID, "rt_intersection_max: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long bits = 0;
+    CU(cudaMemcpy(&bits, ctx->ctr.p + CTR_COUNT, sizeof(bits), cudaMemcpyDeviceToHost));
+    memcpy(out_max, &bits, sizeof(double));
+    return RT_OK;
+}
+
+int rt_divide_device(rt_context* ctx, double* d_values, int64_t count, double divisor, void* stream) {
+    if (!ctx || !d_values || count < 0) return fail(RT_ERR_INVALID, "rt_divide_device: bad argument");
+    if (count == 0) return RT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    unsigned long long bits;
+    memcpy(&bits, &divisor, sizeof(bits));
+    unsigned long long* d_bits = ctx->ctr.p + CTR_COUNT;
+    CU(cudaMemcpyAsync(d_bits, &bits, sizeof(bits), cudaMemcpyHostToDevice, st));
+    k_divide<<<(unsigned)(((size_t)count + 255) / 256), 256, 0, st>>>(d_values, (size_t)count, d_bits);
+    LAUNCHED("k_divide", st);
+    CU(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
 int rt_scene_device_bytes(rt_context* ctx, uint64_t* node_bytes, uint64_t* face_bytes) {
     if (!ctx) return fail(RT_ERR_INVALID, "context is NULL");
     if (node_bytes) *node_bytes = ctx->node_bytes;

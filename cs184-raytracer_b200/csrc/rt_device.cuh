@@ -331,22 +331,20 @@ __device__ __forceinline__ FRay make_fray(d3 o, d3 d) {
     r.bx = -ox * r.ix; r.by = -oy * r.iy; r.bz = -oz * r.iz;
     return r;
 }
-// Entry distance of the (already padded) box, or +inf when missed.  The FMA form has a
-// positional error of a few ulp(|o|) per axis, which the box padding (2e-6 x the largest
-// scene coordinate, rt_bvh.cu) covers; tmax is widened and tmin narrowed by a few ulps and
-// tmin is compared against a widened limit, so FP32 rounding can only let MORE boxes
-// through, never fewer.  (Explicit __fmaf_rn: this file is compiled with -fmad=false.)
+// Entry distance of the (already padded) box, or +inf when missed.  Every FP32 rounding in
+// here (conversion of o and d, 1/d, the FMA) moves a plane distance by the equivalent of at
+// most a few 1e-7 x the largest scene coordinate in position, which the box padding
+// (2e-6 x that coordinate, rt_bvh.cu) covers, and tlimit is already rounded up with slack
+// (prune_limit), so rounding can only let MORE boxes through, never fewer.
+// (Explicit __fmaf_rn: this file is compiled with -fmad=false.)
 __device__ __forceinline__ float slab(const FRay& r, float lx, float ly, float lz, float hx, float hy, float hz,
                                       float tlimit) {
     float t0x = __fmaf_rn(lx, r.ix, r.bx), t1x = __fmaf_rn(hx, r.ix, r.bx);
     float t0y = __fmaf_rn(ly, r.iy, r.by), t1y = __fmaf_rn(hy, r.iy, r.by);
     float t0z = __fmaf_rn(lz, r.iz, r.bz), t1z = __fmaf_rn(hz, r.iz, r.bz);
-    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    tmax = __fmaf_rn(fabsf(tmax), 1e-6f, tmax) + 1e-30f;
-    tmin = __fmaf_rn(fabsf(tmin), -1e-6f, tmin);
-    bool hit = (tmin <= tmax) && (tmax >= 0.f) && (tmin <= tlimit);
-    return hit ? fmaxf(tmin, 0.f) : __int_as_float(0x7f800000);
+    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tlimit));
+    return tmin <= tmax ? tmin : __int_as_float(0x7f800000);
 }
 
 #define RT_STACK 96
@@ -397,8 +395,10 @@ struct Trav {
             if (COUNT) wc.nodes += 4;
             const float t0 = slab(fr, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tlim);
             const float t1 = slab(fr, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tlim);
-            const float t2 = slab(fr, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tlim);
-            const float t3 = slab(fr, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tlim);
+            // slots 2 and 3 may be empty (ref == BVH_DONE, NaN box: min/max would ignore the NaNs)
+            const float INFT = __int_as_float(0x7f800000);
+            const float t2 = ref.z != BVH_DONE ? slab(fr, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tlim) : INFT;
+            const float t3 = ref.w != BVH_DONE ? slab(fr, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tlim) : INFT;
             if (ANYHIT && RT_ANYHIT_UNSORTED) {
                 // occlusion query: any order will do; take the first hit slot, defer the others
                 const float INF = __int_as_float(0x7f800000);

@@ -208,6 +208,12 @@ int     rt_unpack_tiles_rgb8(rt_context* ctx, const rt_params* p, const uint8_t*
 int     rt_unpack_tiles(rt_context* ctx, const rt_params* p, const double* d_packed,
                         double* d_frame, void* stream);
 
+/* --intersection-only across ranks (src/scene.cpp:50-58 divides by the GLOBAL maximum): with
+ * tile_world > 1 a render leaves 1/dist^2 un-normalised; the caller max-all-reduces
+ * rt_intersection_max() over the ranks and applies rt_divide_device() to its buffer. */
+int     rt_intersection_max(rt_context* ctx, double* out_max);
+int     rt_divide_device(rt_context* ctx, double* d_values, int64_t count, double divisor, void* stream);
+
 /* ---- parity / measurement exports --------------------------------------- */
 /* Primary-ray hit ids of the last render's camera rays:
  * geom = index in Scene::geometries_, face = index in Mesh::faces_

@@ -224,3 +224,28 @@ def test_progress_callback_contract(pkg, gpu_renderer, scenes):
     assert calls[-1][:2] == (640 * 480, 640 * 480)
     assert all(a[0] <= b[0] for a, b in zip(calls, calls[1:]))
     assert all(c[2] == main_thread for c in calls)
+
+
+def test_intersection_only_across_ranks(pkg, gpu_renderer, scenes):
+    """--intersection-only with tile sharding: per-rank maxima are reduced by the caller
+    (an all-reduce in a real multi-GPU run) before the divide; result == single-rank frame."""
+    import torch
+    gpu_renderer.upload(scenes("input-02"))
+    w, h, world = 200, 120, 3
+    full = gpu_renderer.render(w, h, 10, intersection_only=True)
+    p0 = pkg.make_params(w, h, 10, intersection_only=True, tile_rank=0, tile_world=world)
+    _, max_tiles, _ = pkg.tile_counts(p0)
+    n = max_tiles * pkg.RT_TILE_PIXELS * 3
+    packed = torch.zeros(world, n, dtype=torch.float64, device="cuda")
+    maxima = []
+    for rank in range(world):
+        p = pkg.make_params(w, h, 10, intersection_only=True, tile_rank=rank, tile_world=world)
+        gpu_renderer.render_device(p, packed[rank].data_ptr())
+        maxima.append(gpu_renderer.intersection_max())
+    gmax = max(maxima)
+    for rank in range(world):
+        gpu_renderer.divide_device(packed[rank].data_ptr(), n, gmax)
+    frame = torch.empty(h, w, 3, dtype=torch.float64, device="cuda")
+    gpu_renderer.unpack_tiles(p0, packed.data_ptr(), frame.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy(), full)
