@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "rt_bvh.h"
+#include "rt_sort.cuh"
 
 namespace rt {
 
@@ -110,92 +111,6 @@ __global__ void k_morton(const float* __restrict__ lo, const float* __restrict__
     }
     keys[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
     vals[i] = i;
-}
-
-// ---- LSD radix sort, 8-bit digits, stable ------------------------------------------
-#define SORT_THREADS 256
-#define SORT_WARPS (SORT_THREADS / 32)
-
-__global__ void k_sort_hist(const uint32_t* __restrict__ keys, int n, int chunk, int shift, int nblocks,
-                            int* __restrict__ hist /*[256][nblocks]*/) {
-    __shared__ int sh[256];
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-    int begin = blockIdx.x * chunk, end = min(begin + chunk, n);
-    for (int i = begin + threadIdx.x; i < end; i += SORT_THREADS) atomicAdd(&sh[(keys[i] >> shift) & 255], 1);
-    __syncthreads();
-    hist[threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
-}
-
-// exclusive scan of `count` ints (count <= 65536) by ONE block of 1024 threads
-__global__ void k_sort_scan(int* __restrict__ data, int count) {
-    __shared__ int warp_sums[32];
-    const int per = (count + 1023) / 1024;
-    int begin = threadIdx.x * per, end = min(begin + per, count);
-    int sum = 0;
-    for (int i = begin; i < end; i++) sum += data[i];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        int ws = warp_sums[lane];
-        int wi = ws;
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
-        }
-        warp_sums[lane] = wi - ws;
-    }
-    __syncthreads();
-    int run = warp_sums[w] + incl - sum;
-    for (int i = begin; i < end; i++) {
-        int v = data[i];
-        data[i] = run;
-        run += v;
-    }
-}
-
-__global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
-                               uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int n, int chunk,
-                               int shift, int nblocks, const int* __restrict__ offsets) {
-    __shared__ int base[256];
-    __shared__ int warp_cnt[SORT_WARPS][256];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    base[tid] = offsets[tid * nblocks + blockIdx.x];
-    for (int k = 0; k < SORT_WARPS; k++) warp_cnt[k][tid] = 0;
-    __syncthreads();
-    int begin = blockIdx.x * chunk, end = min(begin + chunk, n);
-    for (int tile = begin; tile < end; tile += SORT_THREADS) {
-        int i = tile + tid;
-        bool valid = i < end;
-        uint32_t key = valid ? keys_in[i] : 0u;
-        int val = valid ? vals_in[i] : 0;
-        uint32_t digit = valid ? ((key >> shift) & 255u) : (0x10000u + lane);
-        unsigned peers = __match_any_sync(0xffffffffu, digit);
-        int rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) warp_cnt[w][digit] = __popc(peers);
-        __syncthreads();
-        if (valid) {
-            int off = 0;
-            for (int k = 0; k < w; k++) off += warp_cnt[k][digit];
-            int pos = base[digit] + off + rank;
-            keys_out[pos] = key;
-            vals_out[pos] = val;
-        }
-        __syncthreads();
-        int tot = 0;
-        for (int k = 0; k < SORT_WARPS; k++) {
-            tot += warp_cnt[k][tid];
-            warp_cnt[k][tid] = 0;
-        }
-        base[tid] += tot;
-        __syncthreads();
-    }
 }
 
 // ---- Karras 2012 ---------------------------------------------------------------------
@@ -428,22 +343,10 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
             }
             const int gblk = (gn + T - 1) / T;
             // radix sort of this group's (key, prim index) pairs: 4 passes x 8 bits
-            int sblocks = (gn + 4095) / 4096;
-            if (sblocks > 256) sblocks = 256;
-            int chunk = (gn + sblocks - 1) / sblocks;
-            chunk = (chunk + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
             uint32_t *kin = keys0 + gs, *kout = keys1 + gs;
             int *vin = vals0 + gs, *vout = vals1 + gs;
-            for (int pass = 0; pass < 4; pass++) {
-                int shift = pass * 8;
-                k_sort_hist<<<sblocks, SORT_THREADS, 0, stream>>>(kin, gn, chunk, shift, sblocks, hist);
-                k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * sblocks);
-                k_sort_scatter<<<sblocks, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, gn, chunk, shift, sblocks, hist);
-                (*launches) += 3;
-                uint32_t* tk = kin; kin = kout; kout = tk;
-                int* tv = vin; vin = vout; vout = tv;
-            }
-            // after 4 passes the sorted data is back in keys0/vals0
+            sort_pairs(stream, kin, kout, vin, vout, hist, gn, nullptr, 32, launches);
+            // kin/vin now point at the sorted data
             k_karras<<<gblk, T, 0, stream>>>(kin, gn, left + gs, right + gs, pint + gs, pleaf + gs);
             k_refit<<<gblk, T, 0, stream>>>(gn, vin, plo, phi, left + gs, right + gs, pint + gs, pleaf + gs,
                                             ilo + 3 * (size_t)gs, ihi + 3 * (size_t)gs, flags + gs);

@@ -55,6 +55,7 @@ def full(rep, dst, cmd):
     mixes = []
     for a, b in zip(starts[:-1], starts[1:]):
         h, data = srows[a + 1], srows[a + 2:b]
+        sec_name = srows[a][1]
         isrc, ismp, iex, ith = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
         smp, ex, th = collections.Counter(), collections.Counter(), collections.Counter()
         for r in data:
@@ -67,7 +68,7 @@ def full(rep, dst, cmd):
             toks = r[isrc].split()
             op = (toks[1] if toks and toks[0].startswith("@") else toks[0]).split(".")[0] if toks else "?"
             smp[op] += s; ex[op] += e; th[op] += t
-        mixes.append((smp, ex, th))
+        mixes.append((sec_name, smp, ex, th))
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary\n\n`{cmd}`\n\n")
         for k, row in enumerate(rows[2:]):
@@ -80,8 +81,11 @@ def full(rep, dst, cmd):
             f.write("\nwarp stall reasons (warps per issue-active cycle): " + ", ".join(
                 f"{k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} {v:.2f}"
                 for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8]) + "\n\n")
-            if k < len(mixes):
-                smp, ex, th = mixes[k]
+            kname = row[hdr.index('Kernel Name')].split('(')[0].replace('void ', '')
+            cand = [m for m in mixes if kname.split('<')[0] in m[0]]
+            nth = sum(1 for r2 in rows[2:2 + k] if r2[hdr.index('Kernel Name')].split('(')[0].replace('void ', '') == kname)
+            if cand:
+                _, smp, ex, th = cand[min(nth, len(cand) - 1)]
                 te, ts = sum(ex.values()), sum(smp.values())
                 f.write(f"SASS mix (warp-instructions {te}, avg active threads {sum(th.values()) / max(te, 1):.1f}):\n\n| opcode | % instr | % samples | avg threads |\n|---|---|---|---|\n")
                 for op, e in ex.most_common(16):
