@@ -121,6 +121,7 @@ struct rt_context {
     DevBuf<DLight> slights, alights;
     DevBuf<double2> face_pts, face_nrm;
     DevBuf<int> flat, all_prims, bvh_prims;
+    DevBuf<float4> sph_bound;
     DevBuf<BvhNode> nodes;
     DeviceArena scratch;                    // upload / LBVH-build temporaries
     // render state
@@ -254,6 +255,37 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
         d.num_faces = (int)g.num_faces;
         d.use_bbox = g.use_bbox;
     }
+    // world-space bounding spheres of the SPHERE geometries (FP32 pre-test, rt_device.cuh)
+    std::vector<float4> hsb((size_t)ng, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < ng; i++) {
+        const rt_geometry& g = s->geometries[i];
+        if (g.type != RT_GEOM_SPHERE) continue;
+        double c[3], B[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};     // B = A^T A, A = linear part of fwd
+        for (int a = 0; a < 3; a++) {
+            c[a] = g.fwd[4 * a] * g.center[0] + g.fwd[4 * a + 1] * g.center[1] + g.fwd[4 * a + 2] * g.center[2] + g.fwd[4 * a + 3];
+            for (int i2 = 0; i2 < 3; i2++)
+                for (int j2 = 0; j2 < 3; j2++) B[i2][j2] += g.fwd[4 * a + i2] * g.fwd[4 * a + j2];
+        }
+        // largest eigenvalue of the symmetric 3x3 B (trigonometric closed form) = sigma_max(A)^2
+        double lmax;
+        const double p1 = B[0][1] * B[0][1] + B[0][2] * B[0][2] + B[1][2] * B[1][2];
+        if (p1 == 0) {
+            lmax = std::fmax(B[0][0], std::fmax(B[1][1], B[2][2]));
+        } else {
+            const double q = (B[0][0] + B[1][1] + B[2][2]) / 3;
+            const double p2 = (B[0][0] - q) * (B[0][0] - q) + (B[1][1] - q) * (B[1][1] - q) + (B[2][2] - q) * (B[2][2] - q) + 2 * p1;
+            const double p = std::sqrt(p2 / 6);
+            double C[3][3];
+            for (int i2 = 0; i2 < 3; i2++)
+                for (int j2 = 0; j2 < 3; j2++) C[i2][j2] = (B[i2][j2] - (i2 == j2 ? q : 0)) / p;
+            double detC = C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0]) +
+                          C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]);
+            double r = std::fmin(1.0, std::fmax(-1.0, detC / 2));
+            lmax = q + 2 * p * std::cos(std::acos(r) / 3);
+        }
+        double rw = std::fabs(g.radius) * std::sqrt(std::fmax(lmax, 0.0)) * (1.0 + 1e-6);
+        hsb[(size_t)i] = make_float4((float)c[0], (float)c[1], (float)c[2], std::nextafter((float)rw, INFINITY));
+    }
     for (int i = 0; i < s->num_materials; i++) {
         const rt_material& m = s->materials[i];
         DMat& d = hm[(size_t)i];
@@ -356,6 +388,8 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     CU(ctx->mats.ensure(hm.size()));
     CU(ctx->slights.ensure(hsl.size()));
     CU(ctx->alights.ensure(hal.size()));
+    CU(ctx->sph_bound.ensure((size_t)ng));
+    if (ng) CU(cudaMemcpyAsync(ctx->sph_bound.p, hsb.data(), sizeof(float4) * hsb.size(), cudaMemcpyHostToDevice, st));
     CU(ctx->flat.ensure(flat_codes.size()));
     CU(ctx->all_prims.ensure(all_codes.size()));
     CU(ctx->bvh_prims.ensure(bvh_codes.size()));
@@ -404,6 +438,7 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     S.face_nrm = ctx->face_nrm.p;
     S.flat = ctx->flat.p;
     S.all_prims = ctx->all_prims.p;
+    S.sph_bound = ctx->sph_bound.p;
     S.num_geoms = ng;
     S.num_slights = (int)hsl.size();
     S.num_alights = (int)hal.size();
