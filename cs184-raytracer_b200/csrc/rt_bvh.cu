@@ -215,12 +215,10 @@ __global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __re
     }
     float lo[3][4], hi[3][4];
     int ref[4];
-    // empty slots get NaN boxes: every comparison of the slab test is false, so they never
-    // hit (an "inverted" box would: min/max make the slab test symmetric in lo/hi)
-    const float QNAN = __int_as_float(0x7fc00000);
+    // empty slots get inverted boxes, which the sign-ordered slab test never hits (rt_device.cuh)
     for (int k = 0; k < 4; k++) {
         if (k >= ns) {
-            for (int a = 0; a < 3; a++) { lo[a][k] = QNAN; hi[a][k] = QNAN; }
+            for (int a = 0; a < 3; a++) { lo[a][k] = BVH_EMPTY_LO; hi[a][k] = BVH_EMPTY_HI; }
             ref[k] = BVH_DONE;
             continue;
         }
@@ -363,11 +361,10 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
         CK(cudaGetLastError());
         if (nsuper > 0) {
             const float pad = 2e-6f * fmaxf(pad_scale, 1e-30f);
-            const float QNAN = NAN;         // empty slots: never hit (see k_pack_wide)
             float lo[3][4], hi[3][4];
             int ref[4];
             for (int k = 0; k < 4; k++) {
-                for (int a = 0; a < 3; a++) { lo[a][k] = QNAN; hi[a][k] = QNAN; }
+                for (int a = 0; a < 3; a++) { lo[a][k] = BVH_EMPTY_LO; hi[a][k] = BVH_EMPTY_HI; }
                 ref[k] = BVH_DONE;
                 if (k >= K) continue;
                 ref[k] = groups[k].root_ref;

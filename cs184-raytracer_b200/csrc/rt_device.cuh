@@ -20,6 +20,14 @@
 
 #include "rt_b200.h"
 
+// build-time tunables (A/B'd on B200 with tools/ab.sh)
+#ifndef RT_PREFETCH_PUSH
+#define RT_PREFETCH_PUSH 0
+#endif
+#ifndef RT_NOINLINE_PRIM
+#define RT_NOINLINE_PRIM 0
+#endif
+
 namespace rt {
 
 struct d3 {
@@ -110,17 +118,22 @@ struct DCamera {
 // Normals: n0.xy | n0.z n1.x | n1.yz | n2.xy | n2.z pad.
 #define RT_FACE_D2 5
 
-// 4-wide LBVH node, 128 B = 8 x float4: the four child boxes as SoA (FP32, padded outward)
-// + four child references.  ref >= 0: wide-node index; ref < 0: leaf, prim code = ~ref;
-// empty slot: ref = BVH_DONE with a NaN box (never hit).  A wide node is a binary
-// Karras node at even depth with its grandchildren pulled up, which halves the number of
-// dependent fetches per ray (the traversal kernels are latency-bound).
-struct alignas(16) BvhNode {
+// 4-wide LBVH node, 128 B = 8 x float4 (128-byte aligned): the four child boxes as SoA (FP32,
+// padded outward) + four child references.  ref >= 0: wide-node index; ref < 0: leaf, prim
+// code = ~ref; empty slot: ref = BVH_DONE with an INVERTED box (lo = +1e30, hi = -1e30), which
+// the sign-ordered slab test below can never hit.  A wide node is a binary Karras node at even
+// depth with its grandchildren pulled up, which halves the number of dependent fetches per ray.
+// The lower planes sit in the first 64 bytes and the upper planes in the second, 64 bytes
+// apart: a ray fetches its NEAR plane of an axis from one half and the FAR plane from the same
+// offset in the other half (address ^ 64), chosen once per ray from the sign of its direction.
+struct alignas(128) BvhNode {
     float4 lox, loy, loz;
-    float4 hix, hiy, hiz;
     int4 ref;
+    float4 hix, hiy, hiz;
     int4 pad_;
 };
+#define BVH_EMPTY_LO 1e30f
+#define BVH_EMPTY_HI (-1e30f)
 #define BVH_DONE ((int)0x80000000)     // not a valid ref (prim codes stay below 3<<29)
 
 // prim code: kind in the top 2 bits of a 31-bit value
@@ -307,8 +320,13 @@ __device__ __forceinline__ bool sphere_certainly_missed(float4 bs, d3 o, d3 d) {
 }
 
 // Dispatch one prim code.  Returns true only for ANYHIT occlusion.
+#if RT_NOINLINE_PRIM
+#define RT_PRIM_INLINE __noinline__
+#else
+#define RT_PRIM_INLINE __forceinline__
+#endif
 template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ bool test_prim(const DScene& S, int code, d3 o, d3 d, bool reverse, double limit,
+__device__ RT_PRIM_INLINE bool test_prim(const DScene& S, int code, d3 o, d3 d, bool reverse, double limit,
                                           ObjRay& R, Best& best, WorkCounters& wc) {
     const int kind = code >> PRIM_KIND_SHIFT, idx = code & PRIM_INDEX_MASK;
     if (kind == PRIM_SPHERE) {
@@ -336,6 +354,9 @@ __device__ __forceinline__ bool test_prim(const DScene& S, int code, d3 o, d3 d,
 struct FRay {
     float ix, iy, iz;      // 1/d (clamped away from 0)
     float bx, by, bz;      // -o/d, so that t = plane * (1/d) + (-o/d) is one FMA
+    // byte offset, inside a node, of this ray's NEAR plane per axis (lower plane when the
+    // direction component is >= 0, upper plane otherwise); the far plane is at address ^ 64
+    unsigned nx, ny, nz;
 };
 __device__ __forceinline__ FRay make_fray(d3 o, d3 d) {
     FRay r;
@@ -347,27 +368,49 @@ __device__ __forceinline__ FRay make_fray(d3 o, d3 d) {
     if (fabsf(dz) < tiny) dz = copysignf(tiny, dz);
     r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
     r.bx = -ox * r.ix; r.by = -oy * r.iy; r.bz = -oz * r.iz;
+    r.nx = r.ix < 0.f ? 64u : 0u;
+    r.ny = r.iy < 0.f ? 80u : 16u;
+    r.nz = r.iz < 0.f ? 96u : 32u;
+    // opaque, or the compiler re-derives the three offsets from the direction signs per node visit
+    asm volatile("" : "+r"(r.nx), "+r"(r.ny), "+r"(r.nz));
     return r;
 }
-// Entry distance of the (already padded) box, or +inf when missed.  Every FP32 rounding in
-// here (conversion of o and d, 1/d, the FMA) moves a plane distance by the equivalent of at
-// most a few 1e-7 x the largest scene coordinate in position, which the box padding
-// (2e-6 x that coordinate, rt_bvh.cu) covers, and tlimit is already rounded up with slack
-// (prune_limit), so rounding can only let MORE boxes through, never fewer.
+// Entry distance of four (already padded) boxes.  near/far planes are picked by the sign of
+// the direction, so t_near <= t_far per axis by construction (x -> fma(x, i, b) is monotone)
+// and the test is  max(t_near, 0) <= min(t_far, tlimit).  Every FP32 rounding in here
+// (conversion of o and d, 1/d, the FMA) moves a plane distance by the equivalent of at most a
+// few 1e-7 x the largest scene coordinate in position, which the box padding (2e-6 x that
+// coordinate, rt_bvh.cu) covers, and tlimit is already rounded up with slack (prune_limit), so
+// rounding can only let MORE boxes through, never fewer.  An empty slot (inverted box) has
+// t_near >= +1e30 > t_far <= -1e30 on every axis: never hit.
 // (Explicit __fmaf_rn: this file is compiled with -fmad=false.)
-__device__ __forceinline__ float slab(const FRay& r, float lx, float ly, float lz, float hx, float hy, float hz,
-                                      float tlimit) {
-    float t0x = __fmaf_rn(lx, r.ix, r.bx), t1x = __fmaf_rn(hx, r.ix, r.bx);
-    float t0y = __fmaf_rn(ly, r.iy, r.by), t1y = __fmaf_rn(hy, r.iy, r.by);
-    float t0z = __fmaf_rn(lz, r.iz, r.bz), t1z = __fmaf_rn(hz, r.iz, r.bz);
-    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
-    float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tlimit));
-    return tmin <= tmax ? tmin : __int_as_float(0x7f800000);
+struct Slab4 {
+    float tn[4];     // entry distance (clamped to >= 0)
+    bool hit[4];
+};
+__device__ __forceinline__ void slab1(const FRay& r, float nx, float ny, float nz, float fx, float fy, float fz,
+                                      float tlimit, float& tn, bool& hit) {
+    const float tnx = __fmaf_rn(nx, r.ix, r.bx), tny = __fmaf_rn(ny, r.iy, r.by), tnz = __fmaf_rn(nz, r.iz, r.bz);
+    const float tfx = __fmaf_rn(fx, r.ix, r.bx), tfy = __fmaf_rn(fy, r.iy, r.by), tfz = __fmaf_rn(fz, r.iz, r.bz);
+    tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
+    hit = tn <= tf;
 }
 
 #define RT_STACK 96
 #ifndef RT_ANYHIT_UNSORTED
 #define RT_ANYHIT_UNSORTED 1
+#endif
+// Entries of the traversal stack kept in SHARED memory per thread (interleaved by thread, so
+// any mix of stack depths within a warp is bank-conflict free); deeper entries overflow to
+// the local-memory array.  ncu (round 1): with the whole stack in local memory, local
+// loads/stores were 2/3 of all L1 requests of k_shadow and wrote 22 GB per launch through to
+// L2 — the LSU data pipe (75 % busy) was the limiter, not DRAM.
+#ifndef RT_SH_STACK
+#define RT_SH_STACK 12
+#endif
+#ifndef RT_BLOCK
+#define RT_BLOCK 128
 #endif
 
 __device__ __forceinline__ float prune_limit(double x) {
@@ -376,95 +419,158 @@ __device__ __forceinline__ float prune_limit(double x) {
     return __double2float_ru(x) * 1.00001f + 1e-30f;
 }
 
-// Traversal state of one ray over the 4-wide LBVH.  Leaves are deferred through the same
-// stack as internal nodes ("while-while"): descend() only walks internal nodes (cheap FP32
-// slab tests) and returns at a leaf, so the threads of a warp reconverge before the long
-// exact FP64 primitive test instead of diverging into it.
-template <bool ANYHIT>
-struct Trav {
-    int stack[RT_STACK];
-    float tstack[ANYHIT ? 1 : RT_STACK];   // closest hit: entry distance of deferred subtrees
-    int sp;
-    int cur;
+// ---- traversal stack ------------------------------------------------------------------
+// The first RT_SH_STACK entries of a thread's stack live in shared memory, in a column
+// interleaved by thread (entry e of thread t at base + (e * RT_BLOCK + t) * entry size: no
+// bank conflicts whatever the mix of depths in a warp); deeper entries overflow into a
+// local-memory array (rare).  Any-hit entries are a node/leaf reference (4 B); closest-hit
+// entries also carry the subtree's entry distance (8 B).  The state is the shared address of
+// the next free slot (`top`) and the number of overflowed entries (`lsp`, > 0 only while the
+// shared column is full), both plain registers.
+#define RT_SH_ENTRY(ANYHIT) ((ANYHIT) ? 4 : 8)
+#define RT_SH_STRIDE(ANYHIT) (RT_BLOCK * RT_SH_ENTRY(ANYHIT))
+#define RT_SH_STACK_BYTES(ANYHIT) ((RT_SH_STACK > 0 ? RT_SH_STACK : 1) * RT_SH_STRIDE(ANYHIT))
 
-    __device__ __forceinline__ void start() { sp = 0; cur = 0; }   // node 0 is the root
+template <bool ANYHIT>
+__device__ __forceinline__ unsigned stack_base(const void* smem) {
+    unsigned b = (unsigned)__cvta_generic_to_shared(smem) + threadIdx.x * RT_SH_ENTRY(ANYHIT);
+    asm volatile("" : "+r"(b));     // opaque: keep it in a register instead of re-deriving it from %tid per push
+    return b;
+}
+
+// overflow part (local memory) — kept apart from the scalars so that those stay in registers
+template <bool ANYHIT>
+struct StackSpill {
+    int ref[RT_STACK];
+    float t[ANYHIT ? 1 : RT_STACK];
+};
+template <bool ANYHIT>
+struct Stack {
+    // `top`: shared address of the next free slot; it keeps growing (virtually) past `lim`
+    // when the shared column is full, the entries beyond living in the spill arrays
+    unsigned base, top;
+    StackSpill<ANYHIT>& sp;
+    __device__ __forceinline__ Stack(unsigned shbase, StackSpill<ANYHIT>& spill) : base(shbase), top(shbase), sp(spill) {}
+    __device__ __forceinline__ unsigned lim() const { return base + RT_SH_STACK * RT_SH_STRIDE(ANYHIT); }
+    __device__ __forceinline__ static void sts(unsigned a, int ref, float t) {
+        if (ANYHIT) asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(ref));
+        else asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(ref), "r"(__float_as_int(t)));
+    }
+    // room for n more entries in the shared column?
+    __device__ __forceinline__ bool roomy(int n) const { return top + n * RT_SH_STRIDE(ANYHIT) <= lim(); }
+    // push when the caller has checked roomy(): straight-line, predicated by `on`
+    __device__ __forceinline__ void push_fast(bool on, int ref, float t) {
+        if (on) sts(top, ref, t);
+        top += on ? RT_SH_STRIDE(ANYHIT) : 0;
+    }
+    __device__ __forceinline__ void push(int ref, float t) {
+        if (top < lim()) {
+            sts(top, ref, t);
+        } else {
+            const unsigned k = (top - lim()) / RT_SH_STRIDE(ANYHIT);
+            if (k >= RT_STACK) return;            // 3 pushes per wide level, depth <= 31 wide levels
+            sp.ref[k] = ref;
+            if (!ANYHIT) sp.t[k] = t;
+        }
+        top += RT_SH_STRIDE(ANYHIT);
+    }
+    // Pops the next deferred subtree; closest hit: skips those a closer hit has made obsolete.
     __device__ __forceinline__ int pop(float tlim) {
-        while (sp) {
-            --sp;
-            if (ANYHIT || tstack[sp] <= tlim) return stack[sp];   // skip subtrees a closer hit made obsolete
+        while (top != base) {
+            top -= RT_SH_STRIDE(ANYHIT);
+            int ref, tb = 0;
+            if (top < lim()) {
+                if (ANYHIT) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ref) : "r"(top));
+                else asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(top));
+            } else {
+                const unsigned k = (top - lim()) / RT_SH_STRIDE(ANYHIT);
+                ref = sp.ref[k];
+                if (!ANYHIT) tb = __float_as_int(sp.t[k]);
+            }
+            if (ANYHIT || __int_as_float(tb) <= tlim) return ref;
         }
         return BVH_DONE;
     }
-    __device__ __forceinline__ void push(int ref, float t) {
-        if (sp < RT_STACK) {               // 3 pushes per wide level, depth <= 31 wide levels
-            stack[sp] = ref;
-            if (!ANYHIT) tstack[sp] = t;
-            sp++;
-        }
-    }
-    // Walk internal nodes until `cur` is a leaf reference (< 0) or BVH_DONE.
-    template <bool COUNT>
-    __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float tlim, WorkCounters& wc) {
-        while (cur >= 0) {
-            const float4* __restrict__ np = reinterpret_cast<const float4*>(S.nodes + cur);
-            const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
-            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-            const int4 ref = __ldg(reinterpret_cast<const int4*>(np + 6));
-            if (COUNT) wc.nodes += 4;
-            const float t0 = slab(fr, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tlim);
-            const float t1 = slab(fr, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tlim);
-            // slots 2 and 3 may be empty (ref == BVH_DONE, NaN box: min/max would ignore the NaNs)
-            const float INFT = __int_as_float(0x7f800000);
-            const float t2 = ref.z != BVH_DONE ? slab(fr, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tlim) : INFT;
-            const float t3 = ref.w != BVH_DONE ? slab(fr, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tlim) : INFT;
-            if (ANYHIT && RT_ANYHIT_UNSORTED) {
-                // occlusion query: any order will do; take the first hit slot, defer the others
-                const float INF = __int_as_float(0x7f800000);
-                int next = BVH_DONE;
-                if (t3 < INF) next = ref.w;
-                if (t2 < INF) { if (next != BVH_DONE) push(next, 0.f); next = ref.z; }
-                if (t1 < INF) { if (next != BVH_DONE) push(next, 0.f); next = ref.y; }
-                if (t0 < INF) { if (next != BVH_DONE) push(next, 0.f); next = ref.x; }
-                cur = next != BVH_DONE ? next : pop(tlim);
-                continue;
-            }
-            // sort the four (distance, slot) pairs: slot index rides in the two low mantissa
-            // bits (t >= 0, so the float bit patterns order like unsigned ints; +inf = miss)
-            unsigned k0 = (__float_as_uint(t0) & ~3u) | 0u, k1 = (__float_as_uint(t1) & ~3u) | 1u;
-            unsigned k2 = (__float_as_uint(t2) & ~3u) | 2u, k3 = (__float_as_uint(t3) & ~3u) | 3u;
-            unsigned a, b;
-            a = min(k0, k1); b = max(k0, k1); k0 = a; k1 = b;
-            a = min(k2, k3); b = max(k2, k3); k2 = a; k3 = b;
-            a = min(k0, k2); b = max(k0, k2); k0 = a; k2 = b;
-            a = min(k1, k3); b = max(k1, k3); k1 = a; k3 = b;
-            a = min(k1, k2); b = max(k1, k2); k1 = a; k2 = b;
-            const unsigned MISS = 0x7f800000u;
-            auto ref_of = [&](unsigned k) -> int {
-                unsigned i = k & 3u;
-                return i == 0 ? ref.x : (i == 1 ? ref.y : (i == 2 ? ref.z : ref.w));
-            };
-            if (k0 < MISS) {
-                if (k1 < MISS) {
-                    if (k2 < MISS) {
-                        if (k3 < MISS) push(ref_of(k3), __uint_as_float(k3 & ~3u));
-                        push(ref_of(k2), __uint_as_float(k2 & ~3u));
-                    }
-                    push(ref_of(k1), __uint_as_float(k1 & ~3u));
-                }
-                cur = ref_of(k0);
-            } else {
-                cur = pop(tlim);
-            }
-        }
-    }
 };
+
+__device__ __forceinline__ const float4* flip64(const float4* p) {
+    return reinterpret_cast<const float4*>(reinterpret_cast<unsigned long long>(p) ^ 64ull);
+}
+
+// Walks internal nodes of the 4-wide LBVH until `cur` is a leaf reference (< 0) or BVH_DONE.
+// Leaves are deferred through the same stack as internal nodes ("while-while"): this loop
+// only does cheap FP32 slab tests, so the threads of a warp reconverge before the long exact
+// FP64 primitive test instead of diverging into it.
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float tlim, int& cur, Stack<ANYHIT>& st,
+                                        WorkCounters& wc) {
+    while (cur >= 0) {
+        const char* const nb = reinterpret_cast<const char*>(S.nodes);
+        const unsigned off = (unsigned)cur * (unsigned)sizeof(BvhNode);       // node arrays stay below 4 GB (2^25 nodes)
+        const float4* pnx = reinterpret_cast<const float4*>(nb + (off + fr.nx));
+        const float4* pny = reinterpret_cast<const float4*>(nb + (off + fr.ny));
+        const float4* pnz = reinterpret_cast<const float4*>(nb + (off + fr.nz));
+        const float4 nx = __ldg(pnx), ny = __ldg(pny), nz = __ldg(pnz);
+        const float4 fx = __ldg(flip64(pnx)), fy = __ldg(flip64(pny)), fz = __ldg(flip64(pnz));
+        const int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
+        if (COUNT) wc.nodes += 4;
+        float t0, t1, t2, t3;
+        bool h0, h1, h2, h3;
+        slab1(fr, nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, tlim, t0, h0);
+        slab1(fr, nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, tlim, t1, h1);
+        slab1(fr, nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, tlim, t2, h2);
+        slab1(fr, nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, tlim, t3, h3);
+        if (ANYHIT && RT_ANYHIT_UNSORTED) {
+            // occlusion query: any order will do; take the first hit slot, defer the others
+            int next = h3 ? ref.w : BVH_DONE;
+            if (st.roomy(3)) {
+                bool q;
+                q = h2 && next != BVH_DONE; st.push_fast(q, next, 0.f); next = h2 ? ref.z : next;
+                q = h1 && next != BVH_DONE; st.push_fast(q, next, 0.f); next = h1 ? ref.y : next;
+                q = h0 && next != BVH_DONE; st.push_fast(q, next, 0.f); next = h0 ? ref.x : next;
+            } else {
+                if (h2) { if (next != BVH_DONE) st.push(next, 0.f); next = ref.z; }
+                if (h1) { if (next != BVH_DONE) st.push(next, 0.f); next = ref.y; }
+                if (h0) { if (next != BVH_DONE) st.push(next, 0.f); next = ref.x; }
+            }
+            cur = next != BVH_DONE ? next : st.pop(tlim);
+            continue;
+        }
+        // sort the four (distance, slot) pairs: slot index rides in the two low mantissa
+        // bits (t >= 0, so the float bit patterns order like unsigned ints; MISS sorts last)
+        const unsigned MISS = 0x7f800000u;
+        unsigned k0 = h0 ? ((__float_as_uint(t0) & ~3u) | 0u) : MISS, k1 = h1 ? ((__float_as_uint(t1) & ~3u) | 1u) : MISS;
+        unsigned k2 = h2 ? ((__float_as_uint(t2) & ~3u) | 2u) : MISS, k3 = h3 ? ((__float_as_uint(t3) & ~3u) | 3u) : MISS;
+        unsigned a, b;
+        a = min(k0, k1); b = max(k0, k1); k0 = a; k1 = b;
+        a = min(k2, k3); b = max(k2, k3); k2 = a; k3 = b;
+        a = min(k0, k2); b = max(k0, k2); k0 = a; k2 = b;
+        a = min(k1, k3); b = max(k1, k3); k1 = a; k3 = b;
+        a = min(k1, k2); b = max(k1, k2); k1 = a; k2 = b;
+        auto ref_of = [&](unsigned k) -> int {
+            unsigned i = k & 3u;
+            return i == 0 ? ref.x : (i == 1 ? ref.y : (i == 2 ? ref.z : ref.w));
+        };
+        // sorted: k3 < MISS implies k2 < MISS implies k1 < MISS; farthest goes deepest
+        if (st.roomy(3)) {
+            st.push_fast(k3 < MISS, ref_of(k3), __uint_as_float(k3 & ~3u));
+            st.push_fast(k2 < MISS, ref_of(k2), __uint_as_float(k2 & ~3u));
+            st.push_fast(k1 < MISS, ref_of(k1), __uint_as_float(k1 & ~3u));
+        } else {
+            if (k3 < MISS) st.push(ref_of(k3), __uint_as_float(k3 & ~3u));
+            if (k2 < MISS) st.push(ref_of(k2), __uint_as_float(k2 & ~3u));
+            if (k1 < MISS) st.push(ref_of(k1), __uint_as_float(k1 & ~3u));
+        }
+        cur = k0 < MISS ? ref_of(k0) : st.pop(tlim);
+    }
+}
 
 // The closest-hit / any-hit query == Scene::castRay (src/scene.cpp:142-167).
 //   ANYHIT: returns true when an accepted hit with world distance <= limit exists.
 //   BRUTE : ignore the LBVH and test every primitive (debug / parity aid).
 template <bool ANYHIT, bool BRUTE, bool COUNT>
 __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool reverse, double limit, Best& best,
-                                         WorkCounters& wc) {
+                                         WorkCounters& wc, unsigned shbase) {
     best.geom = -1; best.face = -1; best.dobj = 0.0; best.wd = 0.0;
     ObjRay R;
     R.geom = -1; R.box_ok = 1;
@@ -481,15 +587,16 @@ __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool rever
 
     const FRay fr = make_fray(o, d);
     float tlim = ANYHIT ? prune_limit(limit) : __int_as_float(0x7f800000);   // shrinks as closer hits are found
-    Trav<ANYHIT> T;
-    T.start();
+    StackSpill<ANYHIT> spill;
+    Stack<ANYHIT> st(shbase, spill);
+    int cur = 0;                                           // node 0 is the root
     while (true) {
-        T.template descend<COUNT>(S, fr, tlim, wc);
-        if (T.cur == BVH_DONE) break;
-        if (test_prim<ANYHIT, COUNT>(S, ~T.cur, o, d, reverse, limit, R, best, wc)) return true;
+        descend<ANYHIT, COUNT>(S, fr, tlim, cur, st, wc);
+        if (cur == BVH_DONE) break;
+        if (test_prim<ANYHIT, COUNT>(S, ~cur, o, d, reverse, limit, R, best, wc)) return true;
         if (!ANYHIT && best.geom >= 0) tlim = prune_limit(best.wd);
-        T.cur = T.pop(tlim);
-        if (T.cur == BVH_DONE) break;
+        cur = st.pop(tlim);
+        if (cur == BVH_DONE) break;
     }
     return false;
 }

@@ -13,12 +13,18 @@
 
 namespace rt {
 
+#ifndef RT_BLOCK
 #define RT_BLOCK 128
+#endif
 // Minimum resident blocks per SM (= register cap) of the two traversal kernels.  Both are
 // latency-bound gathers: measured on B200 (synthetic 8K frame, same box) k_shadow 210 ms at
 // 116 regs/4 blocks -> 140 ms at 10 blocks, k_trace 76 ms at 148 regs/3 blocks -> 51 ms at 8.
 #ifndef RT_SHADOW_MINBLOCKS
-#define RT_SHADOW_MINBLOCKS 10
+#define RT_SHADOW_MINBLOCKS 8
+#endif
+// Light-major tile of k_shadow (hits); 0 = one tile spanning the whole hit queue.
+#ifndef RT_SHADOW_TILE
+#define RT_SHADOW_TILE 4096
 #endif
 #ifndef RT_TRACE_MINBLOCKS
 #define RT_TRACE_MINBLOCKS 8
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long
 template <bool BRUTE, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S, RayQ q, size_t off, int n, HitQ h,
                                                      unsigned long long* ctr, int* ids_geom, int* ids_face) {
+    __shared__ __align__(16) unsigned char sm_stack[RT_SH_STACK_BYTES(false)];
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = off + (size_t)t;
     bool active = t < n;
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S
         o = mk3(q.fld(0, i), q.fld(1, i), q.fld(2, i));
         d = mk3(q.fld(3, i), q.fld(4, i), q.fld(5, i));
         meta = q.meta[i];
-        cast_ray<false, BRUTE, COUNT>(S, o, d, (meta >> 8) & 1, 0.0, best, wc);
+        cast_ray<false, BRUTE, COUNT>(S, o, d, (meta >> 8) & 1, 0.0, best, wc, stack_base<false>(sm_stack));
         if (ids_geom) { ids_geom[pixel] = best.geom; ids_face[pixel] = best.face; }
     }
     bool hit = active && best.geom >= 0;
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(DScene S, HitQ h, unsigned l
 // One thread per (hit, shadow light): occlusion query + Phong terms of that light.
 template <bool BRUTE, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene S, HitQ h, unsigned long long* ctr, double* fb) {
+    __shared__ __align__(16) unsigned char sm_stack[RT_SH_STACK_BYTES(true)];
     unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned nsl = (unsigned)S.num_slights;
     WorkCounters wc = {0, 0, 0};
@@ -268,8 +276,20 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
         // light-major mapping: a warp = 32 consecutive hits (neighbouring pixels) towards the
         // SAME light, so its shadow rays are coherent; hit-record loads coalesce
         unsigned li, j;
-        if (S.shadow_mode & 1) { li = (unsigned)(t / nhits); j = (unsigned)(t % nhits); }
-        else { j = (unsigned)(t / nsl); li = (unsigned)(t % nsl); }
+        if (S.shadow_mode & 1) {
+#if RT_SHADOW_TILE > 0
+            // ... in tiles of RT_SHADOW_TILE hits: all lights of one tile are processed back to
+            // back, so its hit records (116 B each) are fetched from DRAM once and re-read from
+            // L2 by the other lights instead of streaming the whole queue once per light
+            const unsigned long long tile = t / ((unsigned long long)RT_SHADOW_TILE * nsl);
+            const unsigned long long first = tile * RT_SHADOW_TILE;
+            const unsigned w = (unsigned)min((unsigned long long)RT_SHADOW_TILE, nhits - first);   // hits in this tile
+            const unsigned r = (unsigned)(t - tile * RT_SHADOW_TILE * nsl);
+            li = r / w; j = (unsigned)first + r % w;
+#else
+            li = (unsigned)(t / nhits); j = (unsigned)(t % nhits);
+#endif
+        } else { j = (unsigned)(t / nsl); li = (unsigned)(t % nsl); }
         const DLight* l = S.slights + li;
         d3 P = mk3(h.fld(0, j), h.fld(1, j), h.fld(2, j));
         d3 N = mk3(h.fld(3, j), h.fld(4, j), h.fld(5, j));
@@ -286,13 +306,15 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
             double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
             int inside = (h.meta[j] >> 8) & 1;
             Best best;
-            bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc);
+            bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc, stack_base<true>(sm_stack));
             if (!occluded) {
                 const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
                 d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
                 double att[3];
                 if (point) {
-                    double f = pow(dL, -l->falloff);          // src/lights.h:23-25
+                    // src/lights.h:23-25.  pow(x, +-0) is exactly 1 for every x (IEEE 754 / C Annex F)
+                    const double fo = l->falloff;
+                    double f = fo == 0.0 ? 1.0 : pow(dL, -fo);
                     for (int k = 0; k < 3; k++) att[k] = f * l->color[k];
                 } else {
                     for (int k = 0; k < 3; k++) att[k] = l->color[k];
@@ -300,7 +322,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
                 double di = ndl < 0.0 ? 0.0 : ndl;            // std::max(N.L, 0.0)
                 d3 R = (2 * ndl) * N - L;                     // src/scene.cpp:101-102
                 double mvr = -dot4(V, R);
-                double si = pow(mvr < 0.0 ? 0.0 : mvr, m->sp);
+                // std::pow(std::max(-V.R, 0.0), sp); pow(+0, y > 0) is exactly +0 (C Annex F)
+                const double sp_ = m->sp;
+                double si = (mvr < 0.0 && sp_ > 0.0) ? 0.0 : pow(mvr < 0.0 ? 0.0 : mvr, sp_);
                 int pixel = h.pixel[j];
                 for (int k = 0; k < 3; k++) {
                     double w = h.fld(9 + k, j);
@@ -365,6 +389,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_query(DScene S, long long n, const
                                                      const double* __restrict__ dir,
                                                      const unsigned char* __restrict__ reverse, int* geom, int* face,
                                                      double* dist, double* point, double* normal) {
+    __shared__ __align__(16) unsigned char sm_stack[RT_SH_STACK_BYTES(false)];
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     d3 o = mk3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
@@ -375,7 +400,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_query(DScene S, long long n, const
     if (raw.x == 0 && raw.y == 0 && raw.z == 0) {
         best.geom = -2;
     } else {
-        cast_ray<false, BRUTE, false>(S, o, ray_normalize(raw), reverse ? reverse[i] != 0 : false, 0.0, best, wc);
+        cast_ray<false, BRUTE, false>(S, o, ray_normalize(raw), reverse ? reverse[i] != 0 : false, 0.0, best, wc, stack_base<false>(sm_stack));
     }
     bool hit = best.geom >= 0;
     if (geom) geom[i] = best.geom;
