@@ -111,6 +111,7 @@ struct TileLayout {
 
 struct rt_context {
     int device = 0;
+    int num_sms = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_scene = false;
@@ -126,6 +127,7 @@ struct rt_context {
     DeviceArena scratch;                    // upload / LBVH-build temporaries
     // render state
     size_t cap = 0;                         // ray-queue capacity per level
+    bool cap_fixed = false;                 // pinned by RT_QUEUE_CAP
     std::vector<DevBuf<double>> qf;         // per level: 9*cap doubles
     std::vector<DevBuf<int>> qi;            // per level: 2*cap ints
     DevBuf<double> hf;                      // 13*(cap/2)
@@ -170,12 +172,16 @@ int rt_create(int device, rt_context** out) {
                     device, prop.name, prop.major, prop.minor);
     rt_context* ctx = new rt_context();
     ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
     CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * CTR_COUNT));
     CU(ctx->ctr.ensure(CTR_COUNT + 1));
+    // RT_QUEUE_CAP pins the ray-queue capacity (development / tests of the batching logic);
+    // otherwise render_core sizes it from the frame
     const char* capenv = getenv("RT_QUEUE_CAP");
+    ctx->cap_fixed = capenv != nullptr;
     ctx->cap = capenv ? (size_t)atoll(capenv) : ((size_t)8 << 20);
     if (ctx->cap < 2 * RT_TILE_PIXELS) ctx->cap = 2 * RT_TILE_PIXELS;
     ctx->cap = ctx->cap / (2 * RT_TILE_PIXELS) * (2 * RT_TILE_PIXELS);
@@ -653,6 +659,14 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     const long long nslots = (long long)T.ids.size() * RT_TILE_PIXELS;
     CU(ctx->fb.ensure((size_t)nslots * 3));
+    if (!ctx->cap_fixed) {
+        // One batch per frame when it fits: small launches end in a long latency-bound tail
+        // (measured on B200, 8K synthetic frame: k_trace 52.5 ms with 8 Mi-slot queues, 44.7 ms
+        // with 64 Mi).  64 Mi slots = 5.1 GB per bounce level, 3.7 GB of hit queue.
+        const size_t unit = 2 * RT_TILE_PIXELS, lo = (size_t)1 << 20, hi = (size_t)64 << 20;
+        size_t want = (2 * (size_t)nslots + unit - 1) / unit * unit;
+        ctx->cap = std::min(std::max(want, lo), hi);
+    }
     const size_t maxchunk = ctx->cap / 2;
     CU(ctx->hf.ensure(13 * maxchunk));
     CU(ctx->hi.ensure(3 * maxchunk));

@@ -24,6 +24,9 @@
 #ifndef RT_PREFETCH_PUSH
 #define RT_PREFETCH_PUSH 0
 #endif
+#ifndef RT_DUMMY_LOAD
+#define RT_DUMMY_LOAD 0
+#endif
 #ifndef RT_NOINLINE_PRIM
 #define RT_NOINLINE_PRIM 0
 #endif
@@ -512,7 +515,13 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
         const float4* pnz = reinterpret_cast<const float4*>(nb + (off + fr.nz));
         const float4 nx = __ldg(pnx), ny = __ldg(pny), nz = __ldg(pnz);
         const float4 fx = __ldg(flip64(pnx)), fy = __ldg(flip64(pny)), fz = __ldg(flip64(pnz));
-        const int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
+        int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
+#if RT_DUMMY_LOAD
+        {   // experiment: one more 16-byte fetch per node visit (is the LSU data path the limiter?)
+            const int4 pd = __ldg(reinterpret_cast<const int4*>(nb + off + 112));
+            if (pd.x == 0x12345678) ref.x = pd.y;
+        }
+#endif
         if (COUNT) wc.nodes += 4;
         float t0, t1, t2, t3;
         bool h0, h1, h2, h3;
