@@ -154,6 +154,9 @@ def load_host() -> C.CDLL:
         lib.as2_write_png_rgb8.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
         lib.as2_write_png_f64.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
         lib.as2_quantize_rgb8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        lib.as2_encode_png_rgb8.restype = C.c_int64
+        lib.as2_encode_png_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int64), C.c_char_p, C.c_int]
         _host = lib
     return _host
 
@@ -355,6 +358,23 @@ def quantize_rgb8(rgb: np.ndarray) -> np.ndarray:
     out = np.empty(rgb.shape, dtype=np.uint8)
     load_host().as2_quantize_rgb8(_ptr(rgb), rgb.size, _ptr(out))
     return out
+
+
+def encode_png(rgb8: np.ndarray, threads: int = 1) -> bytes:
+    """The PNG file image the host writer produces, with the deflate work cut into `threads` stripes."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w = rgb8.shape[0], rgb8.shape[1]
+    cap = int(rgb8.size * 1.01) + (1 << 16)
+    out = np.empty(cap, dtype=np.uint8)
+    need = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    n = load_host().as2_encode_png_rgb8(_ptr(rgb8), w, h, threads, _ptr(out), cap, C.byref(need), err, 512)
+    if n == -2:
+        out = np.empty(need.value, dtype=np.uint8)
+        n = load_host().as2_encode_png_rgb8(_ptr(rgb8), w, h, threads, _ptr(out), need.value, C.byref(need), err, 512)
+    if n < 0:
+        raise RtError(err.value.decode())
+    return out[:n].tobytes()
 
 
 def write_png(path, rgb8: np.ndarray):

@@ -114,6 +114,22 @@ int as2_write_png_f64(const char* path, const double* rgb, int width, int height
     return 0;
 }
 
+// Encodes a PNG into a caller-owned buffer with an explicit thread count (tests / ingest
+// benchmark).  Returns the file size, or -1 (error) / -2 (buffer too small: *needed is set).
+int64_t as2_encode_png_rgb8(const uint8_t* rgb, int width, int height, int threads, uint8_t* out, int64_t out_cap,
+                            int64_t* needed, char* err, int errlen) {
+    try {
+        std::vector<uint8_t> file = PNGWriter::encodeRGB8(rgb, width, height, threads, 6);
+        if (needed) *needed = (int64_t)file.size();
+        if ((int64_t)file.size() > out_cap) return -2;
+        std::memcpy(out, file.data(), file.size());
+        return (int64_t)file.size();
+    } catch (const std::exception& e) {
+        setError(err, errlen, e.what());
+        return -1;
+    }
+}
+
 // Quantise like src/writers.cpp:7 (host implementation used by the PNG writer).
 void as2_quantize_rgb8(const double* rgb, int64_t n_values, uint8_t* out) {
     RasterImage image(1, (int)(n_values / 3));

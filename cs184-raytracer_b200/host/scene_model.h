@@ -21,9 +21,12 @@ namespace as2 {
 class ParseException : public std::runtime_error {
 public:
     explicit ParseException(const std::string& msg, int lineno = -1)
-        : std::runtime_error(format(msg, lineno)) {}
+        : std::runtime_error(format(msg, lineno)), lineno_(lineno) {}
+    int line() const { return lineno_; }
     static void showWarning(const std::string& msg, int lineno = -1);
     static std::string format(const std::string& msg, int lineno);
+private:
+    int lineno_;
 };
 class MathException : public std::runtime_error {
 public:

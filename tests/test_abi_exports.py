@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_host_library_exports(pkg):
     lib = pkg.load_host()
     for name in ("as2_scene_load", "as2_scene_synthetic", "as2_write_synthetic", "as2_scene_free", "as2_scene_flatten",
-                 "as2_scene_render", "as2_write_png_rgb8", "as2_write_png_f64", "as2_quantize_rgb8"):
+                 "as2_scene_render", "as2_write_png_rgb8", "as2_write_png_f64", "as2_quantize_rgb8",
+                 "as2_encode_png_rgb8"):
         assert hasattr(lib, name)
 
 

@@ -195,3 +195,108 @@ def test_synthetic_scene_text_equals_in_memory(pkg, tmp_path):
             assert b[key] == val, key
     sha = hashlib.sha256(rti.read_bytes() + obj.read_bytes()).hexdigest()
     assert sha == hashlib.sha256(rti.read_bytes() + obj.read_bytes()).hexdigest()
+
+
+def _decode_png_bytes(data):
+    """Minimal PNG reader for the writer's own subset (8-bit RGB, filter 0): checks every chunk CRC and the
+    zlib stream's adler32 (zlib.decompress does), so a stitching error in the striped encoder cannot hide."""
+    import struct
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(data):
+        (n,) = struct.unpack(">I", data[pos:pos + 4])
+        typ, body = data[pos + 4:pos + 8], data[pos + 8:pos + 8 + n]
+        (crc,) = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+        assert zlib.crc32(typ + body) == crc, typ
+        if typ == b"IHDR":
+            w, h, depth, ctype, comp, flt, lace = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, comp, flt, lace) == (8, 2, 0, 0, 0)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)
+    assert (raw[:, 0] == 0).all()
+    return raw[:, 1:].reshape(h, w, 3)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (64, 64), (257, 130), (1000, 333)])
+@pytest.mark.parametrize("threads", [1, 2, 3, 8, 64])
+def test_png_striped_encoder_is_a_valid_stream(pkg, shape, threads):
+    """the rows are deflated in parallel stripes stitched into ONE zlib stream."""
+    rng = np.random.default_rng(shape[0] * 1000 + threads)
+    img = rng.integers(0, 256, size=(shape[0], shape[1], 3), dtype=np.uint8)
+    img[shape[0] // 2:, :, :] = 17          # a compressible half, so stripes differ in ratio
+    data = pkg.encode_png(img, threads)
+    assert np.array_equal(_decode_png_bytes(data), img)
+    if threads == 1:
+        from PIL import Image
+        import io
+        assert np.array_equal(np.array(Image.open(io.BytesIO(data)).convert("RGB")), img)
+
+
+def test_png_striped_encoder_matches_pil_on_a_rendered_like_frame(pkg, tmp_path):
+    yy, xx = np.mgrid[0:540, 0:960]
+    img = np.stack([(xx * 255 // 959), (yy * 255 // 539), ((xx + yy) % 256)], axis=-1).astype(np.uint8)
+    path = tmp_path / "g.png"
+    pkg.write_png(path, img)                  # default thread count of the box
+    assert np.array_equal(decode_png(path), img)
+
+
+# ---- SURVEY section 8 f-1: the chunked (multi-threaded) .obj parser ---------------------------------
+def _chunked(monkeypatch, threads, chunk_bytes):
+    monkeypatch.setenv("AS2_PARSE_THREADS", str(threads))
+    monkeypatch.setenv("AS2_PARSE_CHUNK_BYTES", str(chunk_bytes))
+
+
+@pytest.mark.parametrize("threads", [2, 3, 7, 16])
+@pytest.mark.parametrize("scene", ["inputs/input-02.rti", "excess_inputs/bunny4.rti", "excess_inputs/test.rti"])
+def test_chunked_obj_parse_equals_serial_and_reference(pkg, reference, monkeypatch, scene, threads):
+    path = scene_path(scene)
+    if not path.exists():
+        pytest.skip(f"{scene} not shipped")
+    theirs = pkg.flat_arrays(reference.flatten(reference.load(path)))
+    _chunked(monkeypatch, threads, 4096)
+    ours = pkg.flat_arrays(pkg.HostScene.load(path).flat)
+    for key, val in theirs.items():
+        if isinstance(val, np.ndarray):
+            assert np.array_equal(ours[key], val), key
+        else:
+            assert ours[key] == val, key
+
+
+@pytest.mark.parametrize("threads", [2, 5])
+@pytest.mark.parametrize("text,msg", BAD_OBJ + [
+    # the reference validates corner k before it parses corner k+1, and reads line by line
+    ("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 9 x\n", "line 4: vertex index out of range"),
+    ("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\nf 1 2 9\nv 1\n", "line 5: vertex index out of range"),
+    ("v 0 0 0\nv 1 0 0\nf 1 2 3\nv 0 1 0\n", "line 3: vertex index out of range"),      # defined too late
+    ("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1\nf 1 2 9\n", "line 4: v requires 3 or 4 parameters"),
+])
+def test_chunked_obj_errors_match_reference(pkg, reference, tmp_path, monkeypatch, text, msg, threads):
+    _write(tmp_path, "m.obj", "# pad pad pad pad\n" * 0 + text)
+    p = _write(tmp_path, "s.rti", "cam 0 0 5 -1 -1 1 1 -1 1 -1 1 1 1 1 1\nobj m.obj\n")
+    with pytest.raises(RuntimeError) as theirs:
+        reference.load(p)
+    _chunked(monkeypatch, threads, 8)
+    with pytest.raises(pkg.RtError) as ours:
+        pkg.HostScene.load(p)
+    assert msg in str(ours.value)
+    assert str(ours.value) == str(theirs.value)
+
+
+def test_chunked_obj_warnings_come_in_line_order_and_stop_at_the_error(pkg, tmp_path, monkeypatch, capfd):
+    body = "v 0 0 0\nv 1 0 0\nv 0 1 0\ng a\nf 1 1 2\ns off\nf 1 2 3\nf 1 2 2\nusemtl m\n"
+    _write(tmp_path, "m.obj", body)
+    p = _write(tmp_path, "s.rti", "cam 0 0 5 -1 -1 1 1 -1 1 -1 1 1 1 1 1\nobj m.obj\n")
+    _chunked(monkeypatch, 4, 8)
+    scene = pkg.HostScene.load(p)
+    assert pkg.flat_arrays(scene.flat)["num_faces"] == 1
+    err = [l for l in capfd.readouterr().err.splitlines() if l.startswith("Warning")]
+    assert err == ["Warning: line 4: unknown obj line type g", "Warning: line 5: degenerate face",
+                   "Warning: line 6: unknown obj line type s", "Warning: line 8: degenerate face",
+                   "Warning: line 9: unknown obj line type usemtl"]
+    _write(tmp_path, "m.obj", body + "f 1 2 7\nfoo\n")
+    with pytest.raises(pkg.RtError):
+        pkg.HostScene.load(p)
+    err2 = [l for l in capfd.readouterr().err.splitlines() if l.startswith("Warning")]
+    assert err2 == err          # nothing after the failing line 10 is reported
