@@ -317,30 +317,39 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     }
 
     // ---- primitive codes: reference order, then the flat / BVH split ----
-    std::vector<int> all_codes, simple_codes, face_geom((size_t)s->num_faces, 0), face_local((size_t)s->num_faces, 0);
-    size_t n_mesh_faces = 0;
-    for (int i = 0; i < ng; i++)
-        if (s->geometries[i].type == RT_GEOM_MESH) n_mesh_faces += (size_t)s->geometries[i].num_faces;
-    all_codes.reserve(n_mesh_faces + (size_t)ng);
+    // Only the per-GEOMETRY bookkeeping is done here; the per-face arrays (geometry / local
+    // index of a face, FACE codes in reference and LBVH order) are expanded on the device by
+    // k_pack_faces from the FaceOwner table.
+    std::vector<int> simple_codes, simple_all_pos;
+    std::vector<FaceOwner> owners;
+    size_t n_all = 0, n_mesh_faces = 0;
     for (int i = 0; i < ng; i++) {
         const rt_geometry& g = s->geometries[i];
-        if (g.type == RT_GEOM_SPHERE) {
-            all_codes.push_back((PRIM_SPHERE << PRIM_KIND_SHIFT) | i);
-            simple_codes.push_back(all_codes.back());
-        } else {
-            for (int64_t f = 0; f < g.num_faces; f++) {
-                face_geom[(size_t)(g.first_face + f)] = i;
-                face_local[(size_t)(g.first_face + f)] = (int)f;
-            }
-            if (g.type == RT_GEOM_TRI) {
-                all_codes.push_back((PRIM_TRI << PRIM_KIND_SHIFT) | i);
-                simple_codes.push_back(all_codes.back());
-            } else {
-                for (int64_t f = 0; f < g.num_faces; f++)
-                    all_codes.push_back((PRIM_FACE << PRIM_KIND_SHIFT) | (int)(g.first_face + f));
-            }
+        if (g.type == RT_GEOM_SPHERE || g.type == RT_GEOM_TRI) {
+            simple_codes.push_back(((g.type == RT_GEOM_SPHERE ? PRIM_SPHERE : PRIM_TRI) << PRIM_KIND_SHIFT) | i);
+            simple_all_pos.push_back((int)n_all);
+            n_all++;
+        }
+        if (g.type != RT_GEOM_SPHERE && g.num_faces > 0) {
+            FaceOwner o;
+            o.geom = i; o.first = (int)g.first_face; o.count = (int)g.num_faces;
+            o.all_off = g.type == RT_GEOM_MESH ? (int)n_all : -1;
+            o.bvh_off = g.type == RT_GEOM_MESH ? (int)n_mesh_faces : -1;     // + n_simple_in_bvh below
+            owners.push_back(o);
+        }
+        if (g.type == RT_GEOM_MESH) {
+            n_all += (size_t)g.num_faces;
+            n_mesh_faces += (size_t)g.num_faces;
         }
     }
+    if (n_all > (size_t)INT32_MAX) return fail(RT_ERR_INVALID, "too many primitives (%zu)", n_all);
+    int first_mesh_face_code = 0;
+    for (const FaceOwner& o : owners)
+        if (o.all_off >= 0) { first_mesh_face_code = (PRIM_FACE << PRIM_KIND_SHIFT) | o.first; break; }
+    std::sort(owners.begin(), owners.end(), [](const FaceOwner& a, const FaceOwner& b) { return a.first < b.first; });
+    for (size_t k = 1; k < owners.size(); k++)
+        if (owners[k].first < owners[k - 1].first + owners[k - 1].count)
+            return fail(RT_ERR_INVALID, "geometries %d and %d share faces", owners[k - 1].geom, owners[k].geom);
     // spheres and `tri`s: few -> tested by every ray in reference order; many -> into the
     // LBVH, except giants (floors) that would bloat its upper levels.
     std::vector<int> flat_codes, bvh_codes;
@@ -384,10 +393,13 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
             else bvh_codes.push_back(simple_codes[k]);
         }
     }
-    const int n_simple_in_bvh = (int)bvh_codes.size();
-    for (int code : all_codes)
-        if ((code >> PRIM_KIND_SHIFT) == PRIM_FACE) bvh_codes.push_back(code);
-    const int group_sizes[2] = {n_simple_in_bvh, (int)bvh_codes.size() - n_simple_in_bvh};
+    const int n_simple_in_bvh = (int)bvh_codes.size();       // bvh_codes: the simple part only (host copy)
+    const size_t n_bvh = (size_t)n_simple_in_bvh + n_mesh_faces;
+    for (FaceOwner& o : owners)
+        if (o.bvh_off >= 0) o.bvh_off += n_simple_in_bvh;
+    const int group_sizes[2] = {n_simple_in_bvh, (int)n_mesh_faces};
+    // first primitive code of each LBVH group (all build_lbvh needs from the host side)
+    const int group_first_code[2] = {n_simple_in_bvh ? bvh_codes[0] : 0, first_mesh_face_code};
 
     // ---- uploads ----
     CU(ctx->geoms.ensure((size_t)ng));
@@ -397,8 +409,8 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     CU(ctx->sph_bound.ensure((size_t)ng));
     if (ng) CU(cudaMemcpyAsync(ctx->sph_bound.p, hsb.data(), sizeof(float4) * hsb.size(), cudaMemcpyHostToDevice, st));
     CU(ctx->flat.ensure(flat_codes.size()));
-    CU(ctx->all_prims.ensure(all_codes.size()));
-    CU(ctx->bvh_prims.ensure(bvh_codes.size()));
+    CU(ctx->all_prims.ensure(n_all));
+    CU(ctx->bvh_prims.ensure(n_bvh));
     CU(ctx->face_pts.ensure((size_t)s->num_faces * RT_FACE_D2));
     CU(ctx->face_nrm.ensure((size_t)s->num_faces * RT_FACE_D2));
     if (ng) CU(cudaMemcpyAsync(ctx->geoms.p, hg.data(), sizeof(DGeom) * hg.size(), cudaMemcpyHostToDevice, st));
@@ -406,27 +418,38 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     if (!hsl.empty()) CU(cudaMemcpyAsync(ctx->slights.p, hsl.data(), sizeof(DLight) * hsl.size(), cudaMemcpyHostToDevice, st));
     if (!hal.empty()) CU(cudaMemcpyAsync(ctx->alights.p, hal.data(), sizeof(DLight) * hal.size(), cudaMemcpyHostToDevice, st));
     if (!flat_codes.empty()) CU(cudaMemcpyAsync(ctx->flat.p, flat_codes.data(), sizeof(int) * flat_codes.size(), cudaMemcpyHostToDevice, st));
-    if (!all_codes.empty()) CU(cudaMemcpyAsync(ctx->all_prims.p, all_codes.data(), sizeof(int) * all_codes.size(), cudaMemcpyHostToDevice, st));
     if (!bvh_codes.empty()) CU(cudaMemcpyAsync(ctx->bvh_prims.p, bvh_codes.data(), sizeof(int) * bvh_codes.size(), cudaMemcpyHostToDevice, st));
     {   // one arena reservation covers the raw-face staging and (afterwards, reused) the LBVH build
         const size_t nf = (size_t)s->num_faces;
-        size_t need_faces = 2 * DeviceArena::padded(72 * nf) + 2 * DeviceArena::padded(4 * nf) + 4096;
-        size_t need_build = lbvh_scratch_bytes(bvh_codes.size());
+        size_t need_faces = 2 * DeviceArena::padded(72 * nf) + DeviceArena::padded(sizeof(FaceOwner) * owners.size()) +
+                            2 * DeviceArena::padded(4 * simple_codes.size()) + 4096;
+        size_t need_build = lbvh_scratch_bytes(n_bvh);
         CU(ctx->scratch.reserve(std::max(need_faces, need_build)));
+    }
+    if (!simple_codes.empty()) {
+        int* d_pos = ctx->scratch.take<int>(simple_codes.size());
+        int* d_code = ctx->scratch.take<int>(simple_codes.size());
+        if (!d_pos || !d_code) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
+        CU(cudaMemcpyAsync(d_pos, simple_all_pos.data(), sizeof(int) * simple_codes.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_code, simple_codes.data(), sizeof(int) * simple_codes.size(), cudaMemcpyHostToDevice, st));
+        k_scatter_codes<<<(unsigned)((simple_codes.size() + 255) / 256), 256, 0, st>>>((int)simple_codes.size(), d_pos, d_code,
+                                                                                    ctx->all_prims.p);
+        launches++;
+        LAUNCHED("k_scatter_codes", st);
     }
     if (s->num_faces) {
         const size_t nf = (size_t)s->num_faces;
         double* raw_p = ctx->scratch.take<double>(nf * 9);
         double* raw_n = ctx->scratch.take<double>(nf * 9);
-        int* fg = ctx->scratch.take<int>(nf);
-        int* fl = ctx->scratch.take<int>(nf);
-        if (!raw_p || !raw_n || !fg || !fl) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
+        FaceOwner* d_owners = ctx->scratch.take<FaceOwner>(owners.size() ? owners.size() : 1);
+        if (!raw_p || !raw_n || !d_owners) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
         CU(cudaMemcpyAsync(raw_p, s->face_points, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(raw_n, s->face_normals, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(fg, face_geom.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(fl, face_local.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, st));
-        k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p, raw_n, fg, fl,
-                                                                  ctx->face_pts.p, ctx->face_nrm.p);
+        if (!owners.empty())
+            CU(cudaMemcpyAsync(d_owners, owners.data(), sizeof(FaceOwner) * owners.size(), cudaMemcpyHostToDevice, st));
+        k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p, raw_n, d_owners, (int)owners.size(),
+                                                                  ctx->face_pts.p, ctx->face_nrm.p, ctx->all_prims.p,
+                                                                  ctx->bvh_prims.p);
         launches++;
         LAUNCHED("k_pack_faces", st);
     }
@@ -449,9 +472,9 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     S.num_slights = (int)hsl.size();
     S.num_alights = (int)hal.size();
     S.num_flat = (int)flat_codes.size();
-    S.num_all = (int)all_codes.size();
-    S.num_bvh_prims = (int)bvh_codes.size();
-    S.single_leaf = bvh_codes.size() == 1 ? bvh_codes[0] : 0;
+    S.num_all = (int)n_all;
+    S.num_bvh_prims = (int)n_bvh;
+    S.single_leaf = n_bvh == 1 ? (n_simple_in_bvh ? bvh_codes[0] : first_mesh_face_code) : 0;
     // bit 0: light-major thread mapping of k_shadow (hit-major otherwise; kept for A/B runs)
     S.shadow_mode = getenv("RT_SHADOW_MODE") ? atoi(getenv("RT_SHADOW_MODE")) : 1;
     CU(cudaEventRecord(ctx->ev1, st));
@@ -460,12 +483,12 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     cudaEvent_t evb;
     CU(cudaEventCreate(&evb));
     size_t node_count = 0;
-    if (bvh_codes.size() >= 2) {
+    if (n_bvh >= 2) {
         float eye_abs = 0.f;
         for (int k = 0; k < 3; k++) eye_abs = fmaxf(eye_abs, (float)fabs(s->camera.eye[k]));
         char err[256] = "";
-        CU(ctx->nodes.ensure(bvh_codes.size() + 2));
-        int brc = build_lbvh(S, ctx->bvh_prims.p, bvh_codes.data(), (int)bvh_codes.size(), group_sizes, 2, eye_abs, st,
+        CU(ctx->nodes.ensure(n_bvh + 2));
+        int brc = build_lbvh(S, ctx->bvh_prims.p, group_first_code, (int)n_bvh, group_sizes, 2, eye_abs, st,
                              ctx->scratch, ctx->nodes.p, &node_count, &launches, err, sizeof(err));
         ctx->scratch.reset();
         if (brc != RT_OK) { cudaEventDestroy(evb); return fail(brc, "LBVH build: %s", err); }
@@ -481,8 +504,8 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     ctx->face_bytes = sizeof(double2) * RT_FACE_D2 * 2 * (size_t)s->num_faces;
     ctx->stats.scene_bytes_h2d = sizeof(DGeom) * hg.size() + sizeof(DMat) * hm.size() +
                                  sizeof(DLight) * (hsl.size() + hal.size()) +
-                                 sizeof(int) * (flat_codes.size() + all_codes.size() + bvh_codes.size()) +
-                                 (size_t)s->num_faces * (2 * 72 + 8);
+                                 sizeof(int) * (flat_codes.size() + 2 * simple_codes.size() + bvh_codes.size()) +
+                                 sizeof(FaceOwner) * owners.size() + (size_t)s->num_faces * (2 * 72);
     ctx->stats.ms_upload = ms0;
     ctx->stats.ms_build = ms1;
     ctx->stats.kernel_launches = (uint64_t)launches;

@@ -270,7 +270,7 @@ __global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __re
 // One LBVH per primitive GROUP (e.g. spheres/`tri`s vs mesh faces), joined under a short
 // chain of super nodes: floating spheres mixed into a height-field's Morton order would
 // otherwise stretch the leaf-level boxes of the mesh over the whole air space.
-int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, const int* group_sizes, int ngroups,
+int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code, int n, const int* group_sizes, int ngroups,
                float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes, size_t* out_count,
                int* launches, char* err, int errlen) {
     *out_count = 0;
@@ -282,7 +282,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
     const int nblk = (n + T - 1) / T;
     int hb[7];
     float pad_scale = 0.f;
-    struct Group { int start, n, root_ref; float box[6]; };
+    struct Group { int start, n, root_ref, first_code; float box[6]; };
     Group groups[4];
     int K = 0;
     size_t total_nodes = 0;
@@ -290,7 +290,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
         if (n < 2 || ngroups > 4) return RT_OK;    // nothing to build (caller tests a single primitive directly)
         int acc = 0;
         for (int g = 0; g < ngroups; g++) {
-            if (group_sizes[g] > 0) { groups[K].start = acc; groups[K].n = group_sizes[g]; K++; }
+            if (group_sizes[g] > 0) { groups[K].start = acc; groups[K].n = group_sizes[g]; groups[K].first_code = group_first_code[g]; K++; }
             acc += group_sizes[g];
         }
         const int nsuper = K > 1 ? 1 : 0;      // one 4-wide super node joins up to four trees
@@ -334,7 +334,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, c
         for (int g = 0; g < K; g++) {
             const int gs = groups[g].start, gn = groups[g].n;
             if (gn == 1) {
-                groups[g].root_ref = ~h_codes[gs];
+                groups[g].root_ref = ~groups[g].first_code;
                 CK(cudaMemcpyAsync(groups[g].box, plo + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
                 CK(cudaMemcpyAsync(groups[g].box + 3, phi + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
                 continue;

@@ -38,12 +38,12 @@ inline size_t lbvh_scratch_bytes(size_t n) {
     return 4 * DeviceArena::padded(12 * n) + 10 * DeviceArena::padded(4 * n) + DeviceArena::padded(4 * 256 * 256) + 4096;
 }
 
-// Builds one LBVH per primitive group over the n primitive codes in d_codes (device; h_codes
-// is the host copy), groups being consecutive ranges of sizes group_sizes[0..ngroups), and
+// Builds one LBVH per primitive group over the n primitive codes in d_codes (device;
+// group_first_code[g] = first code of group g, all the host side needs to know), groups being consecutive ranges of sizes group_sizes[0..ngroups), and
 // joins them under super nodes so that node 0 is always the root, written to `nodes`
 // (caller-allocated).  n < 2 builds nothing (*out_count = 0).  Temporaries come from `arena`.  extra_abs: largest |coordinate| of ray origins outside the
 // primitives (the camera eye), folded into the box padding.  Returns RT_OK or RT_ERR_CUDA.
-int build_lbvh(const DScene& S, const int* d_codes, const int* h_codes, int n, const int* group_sizes, int ngroups,
+int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code, int n, const int* group_sizes, int ngroups,
                float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes /* >= n + ngroups */,
                size_t* out_count, int* launches, char* err, int errlen);
 

@@ -425,17 +425,47 @@ __global__ void k_gather_probe(const float4* __restrict__ data, unsigned long lo
     if (acc == 123.456f) *sink = acc;
 }
 
-// Raw faces (3 points / 3 normals, 9 doubles each) -> 80-byte device records.
+// A geometry that owns faces (TRI or MESH), sorted by first_face: lets the device derive the
+// per-face (geometry, local index) pair and the primitive-code lists instead of the host
+// building and uploading four million-entry arrays per scene upload.
+struct FaceOwner {
+    int geom, first, count;
+    int all_off;      // MESH: position of its first face in all_prims; -1 for a TRI
+    int bvh_off;      // MESH: position of its first face in bvh_prims; -1 for a TRI
+};
+
+// Raw faces (3 points / 3 normals, 9 doubles each) -> 80-byte device records, plus the
+// FACE primitive codes of mesh faces in reference order (all_prims) and LBVH order (bvh_prims).
 __global__ void k_pack_faces(long long nf, const double* __restrict__ pts, const double* __restrict__ nrm,
-                             const int* __restrict__ face_geom, const int* __restrict__ face_local,
-                             double2* __restrict__ out_p, double2* __restrict__ out_n) {
+                             const FaceOwner* __restrict__ owners, int nowners, double2* __restrict__ out_p,
+                             double2* __restrict__ out_n, int* __restrict__ all_prims, int* __restrict__ bvh_prims) {
     long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
+    // owner = last entry with first <= f (if f lies inside its range)
+    int lo = 0, hi = nowners;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (owners[mid].first <= (int)f) lo = mid + 1;
+        else hi = mid;
+    }
+    int fgeom = 0, flocal = 0;
+    if (lo > 0) {
+        const FaceOwner o = owners[lo - 1];
+        if ((int)f - o.first < o.count) {
+            fgeom = o.geom;
+            flocal = (int)f - o.first;
+            if (o.all_off >= 0) {
+                const int code = (PRIM_FACE << PRIM_KIND_SHIFT) | (int)f;
+                all_prims[o.all_off + flocal] = code;
+                bvh_prims[o.bvh_off + flocal] = code;
+            }
+        }
+    }
     const double* p = pts + 9 * f;
     const double* n = nrm + 9 * f;
     d3 p0 = mk3(p[0], p[1], p[2]), p1 = mk3(p[3], p[4], p[5]), p2 = mk3(p[6], p[7], p[8]);
     d3 va = p1 - p0, vb = p2 - p0;    // the per-ray subtractions of src/geometry.cpp:80-81, done once
-    double aux = __hiloint2double(face_local[f], face_geom[f]);
+    double aux = __hiloint2double(flocal, fgeom);
     double2* q = out_p + f * RT_FACE_D2;
     q[0] = make_double2(p0.x, p0.y);
     q[1] = make_double2(p0.z, va.x);
@@ -448,6 +478,12 @@ __global__ void k_pack_faces(long long nf, const double* __restrict__ pts, const
     m[2] = make_double2(n[4], n[5]);
     m[3] = make_double2(n[6], n[7]);
     m[4] = make_double2(n[8], 0.0);
+}
+
+// dst[pos[i]] = code[i]: the (few) sphere / `tri` codes of all_prims
+__global__ void k_scatter_codes(int n, const int* __restrict__ pos, const int* __restrict__ code, int* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[pos[i]] = code[i];
 }
 
 }  // namespace rt

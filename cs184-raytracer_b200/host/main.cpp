@@ -6,6 +6,7 @@
 #include <sys/time.h>
 
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <fstream>
 #include <vector>
@@ -50,6 +51,12 @@ int main(int argc, char* argv[]) {
     }
     std::remove(out.c_str());
 
+    // AS2_TIMING=1: wall-clock phases on stderr (ingest / render incl. upload + read-back / encode)
+    const bool timing = std::getenv("AS2_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     Scene scene;
     for (const std::string& input : programOptions.inputFilenames_) {
         RTIParser parser(scene);
@@ -72,6 +79,8 @@ int main(int argc, char* argv[]) {
     // (src/main.cpp:70-75) and that sequence works here unchanged (AS2_F64_FRAME=1 takes it).  By
     // default the frame is quantised on the device with the writer's rule (src/writers.cpp:7), so
     // 3 bytes per pixel cross PCIe instead of 24 and the host never touches doubles.
+    const double ms_parse = since(t_start);
+    const auto t_render = std::chrono::steady_clock::now();
     progressTimer(true);
     const int W = programOptions.renderWidth_, H = programOptions.renderHeight_;
     const bool f64frame = std::getenv("AS2_F64_FRAME") != nullptr;
@@ -90,12 +99,21 @@ int main(int argc, char* argv[]) {
         return 1;
     }
     progressTimer(false);
+    const double ms_render = since(t_render);
+    const auto t_write = std::chrono::steady_clock::now();
 
     try {
         PNGWriter(out).writeRGB8(rgb8.data(), W, H);
     } catch (const WriteException& e) {
         std::cerr << "Error: " << e.what() << std::endl;
         return 1;
+    }
+    if (timing) {
+        const rt_stats& st = scene.lastStats();
+        std::fprintf(stderr,
+                     "timing: parse %.1f ms | render call %.1f ms (flatten+upload+LBVH+trace+readback; device: upload %.1f, "
+                     "LBVH %.1f, trace %.1f, readback %.1f) | png %.1f ms | total %.1f ms\n",
+                     ms_parse, ms_render, st.ms_upload, st.ms_build, st.ms_trace, st.ms_readback, since(t_write), since(t_start));
     }
     return 0;
 }
