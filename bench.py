@@ -195,7 +195,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="synthetic", choices=sorted(WORKLOADS))
@@ -212,7 +212,8 @@ def main():
     pkg = load_package()
     config = {"workload": f"{args.workload}: {desc}", "width": width, "height": height, "bounce_depth": depth,
               "partition": f"interleaved 32x32 tiles over {world} rank(s), scene replicated",
-              "l2": "working set (225 MB scene + >=0.7 GB ray queue per level) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "no explicit flush: every frame streams its ray and hit queues (80 B / 116 B per record, 10^6..10^8 records per bounce "
+                    "level) through the 126 MB L2 between two uses of any scene data"}
 
     # -------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -248,14 +249,24 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     base_flags = pkg.RT_FLAG_TIME_KERNELS
     p = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world, flags=base_flags)
+    emulate = os.environ.get("RT_BENCH_EMULATE_RANK")      # "r/n": time rank r's share of an n-rank job on one GPU (development aid)
+    if emulate and world == 1:
+        er, en = (int(x) for x in emulate.split("/"))
+        p = pkg.make_params(width, height, depth, tile_rank=er, tile_world=en, flags=base_flags)
+        config["partition"] = f"EMULATED rank {er} of {en} (its tiles only, no gather)"
     own_tiles, max_tiles, total_tiles = pkg.tile_counts(p)
-    if world == 1:
+    if world == 1 and emulate:
+        out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
+        gathered = frame = None
+        args.no_e2e = True
+    elif world == 1:
         out = torch.empty(height * width * 3, dtype=torch.uint8, device=dev)
         gathered = frame = None
     else:
         out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
-        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        # rank r's tiles land in slice r of one buffer: the gather writes them in place (no concatenation pass)
         packed_all = torch.empty(world * out.numel(), dtype=torch.uint8, device=dev) if rank == 0 else None
+        gathered = list(packed_all.chunk(world)) if rank == 0 else None
         frame = torch.empty(height * width * 3, dtype=torch.uint8, device=dev) if rank == 0 else None
 
     def step():
@@ -263,7 +274,6 @@ def main():
         if world > 1:
             dist.gather(out, gathered, dst=0)
             if rank == 0:
-                torch.cat(gathered, out=packed_all)
                 ren.unpack_tiles(p, packed_all.data_ptr(), frame.data_ptr(), rgb8=True, stream=stream)
 
     def sync_all():
@@ -320,7 +330,6 @@ def main():
             if world > 1:
                 dist.gather(out, gathered, dst=0)
                 if rank == 0:
-                    torch.cat(gathered, out=packed_all)
                     ren.unpack_tiles(pe, packed_all.data_ptr(), frame.data_ptr(), rgb8=True, stream=stream)
                     host_frame.copy_(frame, non_blocking=True)
             else:
@@ -349,7 +358,7 @@ def main():
     # ---------------- roofline of the dominant kernel (rank 0)
     roofline = None
     if rank == 0:
-        pc = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world, flags=pkg.RT_FLAG_COUNT_WORK)
+        pc = pkg.make_params(width, height, depth, tile_rank=p.tile_rank, tile_world=p.tile_world, flags=pkg.RT_FLAG_COUNT_WORK)
         ren.render_device(pc, out.data_ptr(), rgb8=True, stream=stream)
         cs = ren.stats()
         names = ["k_trace", "k_shade", "k_shadow", "other"]

@@ -56,6 +56,8 @@ static bool debug_sync() {
         if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "kernel %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
+#define RT_MAX_LEVELS 257     // bounce_depth <= 255 (check_params) -> levels 0..256
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -137,7 +139,12 @@ struct rt_context {
     DevBuf<int> ids_geom, ids_face;
     DevBuf<unsigned long long> ctr;
     DevBuf<unsigned char> staging;          // resolve target for the host-buffer entry points
-    unsigned long long* h_ctr = nullptr;    // pinned
+    // Device counters: [0, CTR_COUNT) legacy block (unused by renders), [CTR_COUNT] the
+    // intersection-only maximum, then one CTR_COUNT block per bounce level (RT_MAX_LEVELS) so
+    // that level l+1 can be enqueued while level l's shadow kernel still reads its own counts.
+    unsigned long long* h_ctr = nullptr;    // pinned: mirror of the level blocks + 2 words for the per-chunk read-back
+    cudaStream_t copy_stream = nullptr;     // counter read-backs that must not wait for k_shadow
+    cudaEvent_t ev_shade = nullptr;
     TileLayout tiles;
     rt_stats stats;
     std::vector<cudaEvent_t> evpool;        // RT_FLAG_TIME_KERNELS: (start, stop) pairs
@@ -176,8 +183,10 @@ int rt_create(int device, rt_context** out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
-    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * CTR_COUNT));
-    CU(ctx->ctr.ensure(CTR_COUNT + 1));
+    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * (RT_MAX_LEVELS * CTR_COUNT + 2)));
+    CU(ctx->ctr.ensure(CTR_COUNT + 1 + RT_MAX_LEVELS * CTR_COUNT));
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_shade, cudaEventDisableTiming));
     // RT_QUEUE_CAP pins the ray-queue capacity (development / tests of the batching logic);
     // otherwise render_core sizes it from the frame
     const char* capenv = getenv("RT_QUEUE_CAP");
@@ -193,6 +202,8 @@ void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_shade) cudaEventDestroy(ctx->ev_shade);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -575,20 +586,20 @@ int ensure_level(rt_context* ctx, int level) {
 }
 
 template <bool BRUTE, bool COUNT>
-int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h) {
+int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h, unsigned long long* lc) {
     LaunchTimer lt(J, 0);
-    k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, h, J.ctx->ctr.p,
+    k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, h, lc,
                                                                             J.ids_geom, J.ids_face);
     J.launches++;
     LAUNCHED("k_trace", J.st);
     return RT_OK;
 }
 template <bool BRUTE, bool COUNT>
-int launch_shadow(RenderJob& J, int n, HitQ h) {
+int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc) {
     unsigned long long threads = (unsigned long long)n * (unsigned)J.ctx->S.num_slights;
     if (!threads) return RT_OK;
     LaunchTimer lt(J, 2);
-    k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, J.st>>>(J.ctx->S, h, J.ctx->ctr.p,
+    k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, J.st>>>(J.ctx->S, h, lc,
                                                                                                  J.ctx->fb.p);
     J.launches++;
     LAUNCHED("k_shadow", J.st);
@@ -607,19 +618,22 @@ int process_level(RenderJob& J, int level, size_t n) {
     h.cap = maxchunk;
     const bool io = J.p->intersection_only != 0;
     const bool ids_only = J.ids_geom != nullptr;
+    // this level's counter block (CTR_HITS / CTR_NEXT are reset per chunk, the rest accumulate)
+    unsigned long long* lc = ctx->ctr.p + (CTR_COUNT + 1) + (size_t)level * CTR_COUNT;
+    unsigned long long* h_pair = ctx->h_ctr + (size_t)RT_MAX_LEVELS * CTR_COUNT;
     for (size_t off = 0; off < n; off += maxchunk) {
         const int m = (int)std::min(maxchunk, n - off);
         RayQ q = level_queue(ctx, level);
-        CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
+        CU(cudaMemsetAsync(lc, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
         int lrc;
-        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, h) : launch_trace<true, false>(J, q, off, m, h);
-        else lrc = J.count ? launch_trace<false, true>(J, q, off, m, h) : launch_trace<false, false>(J, q, off, m, h);
+        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, h, lc) : launch_trace<true, false>(J, q, off, m, h, lc);
+        else lrc = J.count ? launch_trace<false, true>(J, q, off, m, h, lc) : launch_trace<false, false>(J, q, off, m, h, lc);
         if (lrc != RT_OK) return lrc;
         if (ids_only) continue;
         const unsigned blocks = (unsigned)((m + RT_BLOCK - 1) / RT_BLOCK);
         if (io) {
             LaunchTimer lt(J, 1);
-            k_shade_io<<<blocks, RT_BLOCK, 0, J.st>>>(h, ctx->ctr.p, ctx->fb.p, J.maxbits);
+            k_shade_io<<<blocks, RT_BLOCK, 0, J.st>>>(h, lc, ctx->fb.p, J.maxbits);
             J.launches++;
             LAUNCHED("k_shade_io", J.st);
             continue;
@@ -633,16 +647,20 @@ int process_level(RenderJob& J, int level, size_t n) {
         }
         {
             LaunchTimer lt(J, 1);
-            k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, ctx->ctr.p, next, ctx->fb.p);
+            k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, lc, next, ctx->fb.p);
         }
         J.launches++;
         LAUNCHED("k_shade", J.st);
-        if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h) : launch_shadow<true, false>(J, m, h);
-        else lrc = J.count ? launch_shadow<false, true>(J, m, h) : launch_shadow<false, false>(J, m, h);
+        // The hit and spawn counts are final once k_shade is done: read them back on a side
+        // stream while k_shadow runs, so the next level is enqueued before the GPU goes idle.
+        CU(cudaEventRecord(ctx->ev_shade, J.st));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_shade, 0));
+        CU(cudaMemcpyAsync(h_pair, lc, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h, lc) : launch_shadow<true, false>(J, m, h, lc);
+        else lrc = J.count ? launch_shadow<false, true>(J, m, h, lc) : launch_shadow<false, false>(J, m, h, lc);
         if (lrc != RT_OK) return lrc;
-        CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, J.st));
-        CU(cudaStreamSynchronize(J.st));
-        const unsigned long long nhits = ctx->h_ctr[CTR_HITS], nnext = ctx->h_ctr[CTR_NEXT];
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        const unsigned long long nhits = h_pair[CTR_HITS], nnext = h_pair[CTR_NEXT];
         ctx->stats.hits += nhits;
         ctx->stats.rays_shadow += nhits * (unsigned long long)ctx->S.num_slights;
         ctx->stats.rays_secondary += nnext;
@@ -704,6 +722,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     ctx->evused = 0;
     J.ids_geom = nullptr; J.ids_face = nullptr;
     J.maxbits = ctx->ctr.p + CTR_COUNT;
+    const size_t n_ctr = CTR_COUNT + 1 + (size_t)RT_MAX_LEVELS * CTR_COUNT;
     J.launches = 0;
     if (ids_only) {
         CU(ctx->ids_geom.ensure((size_t)nslots));
@@ -717,7 +736,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     stats.rays_primary = stats.rays_shadow = stats.rays_secondary = stats.hits = stats.degenerate_rays = 0;
     for (int k = 0; k < 2; k++) stats.nodes_fetched[k] = stats.tris_tested[k] = stats.spheres_tested[k] = 0;
     for (int k = 0; k < 4; k++) { stats.ms_kernel[k] = 0; stats.launches_kernel[k] = 0; }
-    CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * (CTR_COUNT + 1), st));
+    CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * n_ctr, st));
     if (p->intersection_only) {
         // std::numeric_limits<double>::min() (src/scene.cpp:51)
         const unsigned long long dblmin = 0x0010000000000000ull;
@@ -752,7 +771,9 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         LAUNCHED("k_divide", st);
     }
     CU(cudaEventRecord(ctx->ev1, st));
-    CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, sizeof(unsigned long long) * CTR_COUNT, cudaMemcpyDeviceToHost, st));
+    const int used_levels = std::min(p->bounce_depth + 1, RT_MAX_LEVELS);
+    CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p + CTR_COUNT + 1, sizeof(unsigned long long) * (size_t)used_levels * CTR_COUNT,
+                       cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     float ms = 0;
@@ -766,13 +787,16 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         prim += (long long)w * hgt;
     }
     stats.rays_primary = (uint64_t)prim;
-    stats.degenerate_rays = ctx->h_ctr[CTR_DEGENERATE];
-    stats.nodes_fetched[0] = ctx->h_ctr[CTR_NODES];
-    stats.tris_tested[0] = ctx->h_ctr[CTR_TRIS];
-    stats.spheres_tested[0] = ctx->h_ctr[CTR_SPHERES];
-    stats.nodes_fetched[1] = ctx->h_ctr[CTR_S_NODES];
-    stats.tris_tested[1] = ctx->h_ctr[CTR_S_TRIS];
-    stats.spheres_tested[1] = ctx->h_ctr[CTR_S_SPHERES];
+    for (int l = 0; l < used_levels; l++) {
+        const unsigned long long* c = ctx->h_ctr + (size_t)l * CTR_COUNT;
+        stats.degenerate_rays += c[CTR_DEGENERATE];
+        stats.nodes_fetched[0] += c[CTR_NODES];
+        stats.tris_tested[0] += c[CTR_TRIS];
+        stats.spheres_tested[0] += c[CTR_SPHERES];
+        stats.nodes_fetched[1] += c[CTR_S_NODES];
+        stats.tris_tested[1] += c[CTR_S_TRIS];
+        stats.spheres_tested[1] += c[CTR_S_SPHERES];
+    }
     stats.kernel_launches = J.launches;
     for (size_t k = 0; k + 1 < ctx->evused; k += 2) {
         float kms = 0;

@@ -413,7 +413,7 @@ __device__ __forceinline__ void slab1(const FRay& r, float nx, float ny, float n
 #define RT_SH_STACK 12
 #endif
 #ifndef RT_BLOCK
-#define RT_BLOCK 128
+#define RT_BLOCK 64
 #endif
 
 __device__ __forceinline__ float prune_limit(double x) {

@@ -14,20 +14,22 @@
 namespace rt {
 
 #ifndef RT_BLOCK
-#define RT_BLOCK 128
+#define RT_BLOCK 64
 #endif
-// Minimum resident blocks per SM (= register cap) of the two traversal kernels.  Both are
-// latency-bound gathers: measured on B200 (synthetic 8K frame, same box) k_shadow 210 ms at
-// 116 regs/4 blocks -> 140 ms at 10 blocks, k_trace 76 ms at 148 regs/3 blocks -> 51 ms at 8.
+// 64-thread blocks: the deep bounce levels are small launches (10^5 rays per rank on 8 GPUs),
+// and finer blocks shorten their tail (B200, 1/8 of the 8K frame: 22.21 -> 21.94 ms).
+// Minimum resident blocks per SM (= 64-register cap, 1024 threads per SM) of the two traversal
+// kernels: with fewer warps they stall on node fetches (k_shadow 147 ms at 768 threads/SM vs
+// 111 ms at 1024), with more the node (28 registers) no longer fits and the loop spills.
 #ifndef RT_SHADOW_MINBLOCKS
-#define RT_SHADOW_MINBLOCKS 8
+#define RT_SHADOW_MINBLOCKS 16
 #endif
 // Light-major tile of k_shadow (hits); 0 = one tile spanning the whole hit queue.
 #ifndef RT_SHADOW_TILE
 #define RT_SHADOW_TILE 4096
 #endif
 #ifndef RT_TRACE_MINBLOCKS
-#define RT_TRACE_MINBLOCKS 8
+#define RT_TRACE_MINBLOCKS 16
 #endif
 
 // Ray queue, SoA over `cap` slots.
