@@ -358,6 +358,12 @@ def main():
     # ---------------- roofline of the dominant kernel (rank 0)
     roofline = None
     if rank == 0:
+        # one frame with the kernels strictly serialised: durations per kernel class that add up to the frame
+        # (in the timed region k_shadow of level l runs beside k_trace / k_shade of level l+1)
+        ps = pkg.make_params(width, height, depth, tile_rank=p.tile_rank, tile_world=p.tile_world,
+                             flags=pkg.RT_FLAG_TIME_KERNELS | pkg.RT_FLAG_SERIAL)
+        ren.render_device(ps, out.data_ptr(), rgb8=True, stream=stream)
+        serial = ren.stats()
         pc = pkg.make_params(width, height, depth, tile_rank=p.tile_rank, tile_world=p.tile_world, flags=pkg.RT_FLAG_COUNT_WORK)
         ren.render_device(pc, out.data_ptr(), rgb8=True, stream=stream)
         cs = ren.stats()
@@ -401,6 +407,11 @@ def main():
                     "bytes_per_launch": bytes_frame / n_launch, "ms_per_launch": ms_launch, "launches_per_step": n_launch,
                     "kernel_share_of_step": float(agg["ms_kernel"][dom] / (ms_total if world == 1 else max(agg["ms_kernel"].sum(), 1e-9))),
                     "ms_kernel_per_step": {n: float(v / args.steps) for n, v in zip(names, agg["ms_kernel"])},
+                    "ms_kernel_serial_frame": {n: float(v) for n, v in zip(names, serial["ms_kernel"])},
+                    "ms_serial_frame": float(serial["ms_trace"]),
+                    "note": "ms_kernel_per_step: event-bracketed durations inside the timed region, where k_trace/k_shade of "
+                            "bounce level l+1 run beside k_shadow of level l (k_trace's bracket includes waiting for SMs); "
+                            "ms_kernel_serial_frame: one extra frame with RT_FLAG_SERIAL, classes add up to ms_serial_frame",
                     "node_gather_gbs": gather, "frac_of_node_gather": achieved / gather if gather else None,
                     "node_array_bytes": node_bytes, "face_record_bytes": face_bytes,
                     "work_per_step": {"nodes": cs["nodes_fetched"], "tris": cs["tris_tested"], "spheres": cs["spheres_tested"],

@@ -26,6 +26,7 @@ RT_LIGHT_AMBIENT, RT_LIGHT_POINT, RT_LIGHT_DIRECTIONAL = 0, 1, 2
 RT_FLAG_BRUTE_FORCE = 1
 RT_FLAG_COUNT_WORK = 2
 RT_FLAG_TIME_KERNELS = 4
+RT_FLAG_SERIAL = 8
 RT_TILE_PIXELS = 32 * 32
 
 

@@ -132,8 +132,12 @@ struct rt_context {
     bool cap_fixed = false;                 // pinned by RT_QUEUE_CAP
     std::vector<DevBuf<double>> qf;         // per level: 9*cap doubles
     std::vector<DevBuf<int>> qi;            // per level: 2*cap ints
-    DevBuf<double> hf;                      // 13*(cap/2)
-    DevBuf<int> hi;                         // 3*(cap/2)
+    DevBuf<double> hf[2];                   // hit queues, 13*(cap/2) each: bounce level l uses buffer l & 1
+    DevBuf<int> hi[2];                      // 3*(cap/2) each
+    cudaStream_t shadow_stream = nullptr;   // k_shadow of level l overlaps trace/shade of level l+1
+    cudaEvent_t ev_hq_free[2] = {nullptr, nullptr};   // last k_shadow reading hit buffer b has been enqueued up to here
+    cudaEvent_t ev_join = nullptr;
+    bool hq_pending[2] = {false, false};
     DevBuf<double> fb;                      // framebuffer, slot order
     DevBuf<int> tile_ids;
     DevBuf<int> ids_geom, ids_face;
@@ -186,6 +190,9 @@ int rt_create(int device, rt_context** out) {
     CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * (RT_MAX_LEVELS * CTR_COUNT + 2)));
     CU(ctx->ctr.ensure(CTR_COUNT + 1 + RT_MAX_LEVELS * CTR_COUNT));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->shadow_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) CU(cudaEventCreateWithFlags(&ctx->ev_hq_free[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_shade, cudaEventDisableTiming));
     // RT_QUEUE_CAP pins the ray-queue capacity (development / tests of the batching logic);
     // otherwise render_core sizes it from the frame
@@ -203,6 +210,10 @@ void rt_destroy(rt_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->shadow_stream) cudaStreamDestroy(ctx->shadow_stream);
+    for (int b = 0; b < 2; b++)
+        if (ctx->ev_hq_free[b]) cudaEventDestroy(ctx->ev_hq_free[b]);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_shade) cudaEventDestroy(ctx->ev_shade);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -533,7 +544,7 @@ struct RenderJob {
     rt_context* ctx;
     const rt_params* p;
     cudaStream_t st;
-    bool brute, count, timed;
+    bool brute, count, timed, overlap;
     int* ids_geom;
     int* ids_face;
     unsigned long long* maxbits;   // intersection-only
@@ -545,7 +556,8 @@ struct LaunchTimer {
     RenderJob& J;
     size_t idx = 0;
     bool on;
-    LaunchTimer(RenderJob& j, int cls) : J(j), on(j.timed) {
+    cudaStream_t st;
+    LaunchTimer(RenderJob& j, int cls, cudaStream_t stream = nullptr) : J(j), on(j.timed), st(stream ? stream : j.st) {
         if (!on) return;
         rt_context* c = J.ctx;
         if (c->evused + 2 > c->evpool.size()) {
@@ -559,10 +571,10 @@ struct LaunchTimer {
         idx = c->evused;
         c->evclass[idx / 2] = cls;
         c->evused += 2;
-        cudaEventRecord(c->evpool[idx], J.st);
+        cudaEventRecord(c->evpool[idx], st);
     }
     ~LaunchTimer() {
-        if (on) cudaEventRecord(J.ctx->evpool[idx + 1], J.st);
+        if (on) cudaEventRecord(J.ctx->evpool[idx + 1], st);
     }
 };
 
@@ -595,14 +607,13 @@ int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h, unsigned long 
     return RT_OK;
 }
 template <bool BRUTE, bool COUNT>
-int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc) {
+int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc, cudaStream_t st) {
     unsigned long long threads = (unsigned long long)n * (unsigned)J.ctx->S.num_slights;
     if (!threads) return RT_OK;
-    LaunchTimer lt(J, 2);
-    k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, J.st>>>(J.ctx->S, h, lc,
-                                                                                                 J.ctx->fb.p);
+    LaunchTimer lt(J, 2, st);
+    k_shadow<BRUTE, COUNT><<<(unsigned)((threads + RT_BLOCK - 1) / RT_BLOCK), RT_BLOCK, 0, st>>>(J.ctx->S, h, lc, J.ctx->fb.p);
     J.launches++;
-    LAUNCHED("k_shadow", J.st);
+    LAUNCHED("k_shadow", st);
     return RT_OK;
 }
 
@@ -610,11 +621,16 @@ int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc) {
 int process_level(RenderJob& J, int level, size_t n) {
     rt_context* ctx = J.ctx;
     const size_t maxchunk = ctx->cap / 2;
+    // Hit queue b = level & 1.  k_shadow runs on its own stream: it only reads this level's hit
+    // queue and counters and adds into the framebuffer, so the next level's k_trace / k_shade
+    // (other hit buffer, other counters) run beside it and fill the tail of the small launches.
+    const int b = J.overlap ? (level & 1) : 0;
+    cudaStream_t sst = J.overlap ? ctx->shadow_stream : J.st;
     HitQ h;
-    h.f = ctx->hf.p;
-    h.pixel = ctx->hi.p;
-    h.geom = ctx->hi.p + maxchunk;
-    h.meta = ctx->hi.p + 2 * maxchunk;
+    h.f = ctx->hf[b].p;
+    h.pixel = ctx->hi[b].p;
+    h.geom = ctx->hi[b].p + maxchunk;
+    h.meta = ctx->hi[b].p + 2 * maxchunk;
     h.cap = maxchunk;
     const bool io = J.p->intersection_only != 0;
     const bool ids_only = J.ids_geom != nullptr;
@@ -624,6 +640,11 @@ int process_level(RenderJob& J, int level, size_t n) {
     for (size_t off = 0; off < n; off += maxchunk) {
         const int m = (int)std::min(maxchunk, n - off);
         RayQ q = level_queue(ctx, level);
+        if (J.overlap && ctx->hq_pending[b]) {
+            // the shadow kernel that read this hit buffer (and possibly this counter block) last
+            CU(cudaStreamWaitEvent(J.st, ctx->ev_hq_free[b], 0));
+            ctx->hq_pending[b] = false;
+        }
         CU(cudaMemsetAsync(lc, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
         int lrc;
         if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, h, lc) : launch_trace<true, false>(J, q, off, m, h, lc);
@@ -656,9 +677,14 @@ int process_level(RenderJob& J, int level, size_t n) {
         CU(cudaEventRecord(ctx->ev_shade, J.st));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_shade, 0));
         CU(cudaMemcpyAsync(h_pair, lc, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h, lc) : launch_shadow<true, false>(J, m, h, lc);
-        else lrc = J.count ? launch_shadow<false, true>(J, m, h, lc) : launch_shadow<false, false>(J, m, h, lc);
+        if (J.overlap) CU(cudaStreamWaitEvent(sst, ctx->ev_shade, 0));
+        if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h, lc, sst) : launch_shadow<true, false>(J, m, h, lc, sst);
+        else lrc = J.count ? launch_shadow<false, true>(J, m, h, lc, sst) : launch_shadow<false, false>(J, m, h, lc, sst);
         if (lrc != RT_OK) return lrc;
+        if (J.overlap) {
+            CU(cudaEventRecord(ctx->ev_hq_free[b], sst));
+            ctx->hq_pending[b] = true;
+        }
         CU(cudaStreamSynchronize(ctx->copy_stream));
         const unsigned long long nhits = h_pair[CTR_HITS], nnext = h_pair[CTR_NEXT];
         ctx->stats.hits += nhits;
@@ -709,8 +735,11 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         ctx->cap = std::min(std::max(want, lo), hi);
     }
     const size_t maxchunk = ctx->cap / 2;
-    CU(ctx->hf.ensure(13 * maxchunk));
-    CU(ctx->hi.ensure(3 * maxchunk));
+    const bool overlap = !(p->flags & RT_FLAG_SERIAL) && getenv("RT_NO_OVERLAP") == nullptr && !ids_only && !p->intersection_only;
+    for (int b = 0; b < (overlap ? 2 : 1); b++) {
+        CU(ctx->hf[b].ensure(13 * maxchunk));
+        CU(ctx->hi[b].ensure(3 * maxchunk));
+    }
     rc = ensure_level(ctx, 0);
     if (rc != RT_OK) return rc;
 
@@ -719,6 +748,8 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     J.brute = (p->flags & RT_FLAG_BRUTE_FORCE) != 0;
     J.count = (p->flags & RT_FLAG_COUNT_WORK) != 0;
     J.timed = (p->flags & RT_FLAG_TIME_KERNELS) != 0;
+    J.overlap = overlap;
+    ctx->hq_pending[0] = ctx->hq_pending[1] = false;
     ctx->evused = 0;
     J.ids_geom = nullptr; J.ids_face = nullptr;
     J.maxbits = ctx->ctr.p + CTR_COUNT;
@@ -762,6 +793,10 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
             long long done = std::min<long long>((first + n) * (long long)p->tile_world, total_px - 1);
             cb((int)done, (int)total_px, user);
         }
+    }
+    if (overlap) {      // the shadow stream's framebuffer adds must land before anything reads the frame
+        CU(cudaEventRecord(ctx->ev_join, ctx->shadow_stream));
+        CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
     if (p->intersection_only && !ids_only && p->tile_world == 1) {
         // global max normalisation (src/scene.cpp:50-58); with tile_world > 1 the caller

@@ -122,6 +122,10 @@ typedef struct rt_scene {
 #define RT_FLAG_COUNT_WORK    2u  /* instrumented build of the same kernels: count nodes /
                                      primitives fetched for the roofline (slower)          */
 #define RT_FLAG_TIME_KERNELS  4u  /* bracket every launch with CUDA events (rt_stats.ms_kernel) */
+#define RT_FLAG_SERIAL        8u  /* run a frame's kernels strictly one after another: by default the
+                                     shadow kernel of bounce level l runs beside the closest-hit and
+                                     shading kernels of level l+1 (their event-bracketed durations
+                                     then overlap and do not add up to the frame time)          */
 
 typedef struct rt_params {
     int32_t  width;              /* programOptions.renderWidth_   (src/options.h:13) */

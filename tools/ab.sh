@@ -10,7 +10,7 @@ for v in "$@"; do
 import json, sys
 try:
     d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
-    k = d["roofline"]["ms_kernel_per_step"]
+    k = d["roofline"].get("ms_kernel_serial_frame") or d["roofline"]["ms_kernel_per_step"]
     print(f"{sys.argv[1]:10s} {d['value']:8.1f} Mrays/s  {d['ms_per_step']:8.2f} ms  " + "  ".join(f"{a} {b:.1f}" for a, b in k.items()))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
