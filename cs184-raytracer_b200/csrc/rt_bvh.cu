@@ -272,7 +272,7 @@ __global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __re
 // otherwise stretch the leaf-level boxes of the mesh over the whole air space.
 int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code, int n, const int* group_sizes, int ngroups,
                float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes, size_t* out_count,
-               int* launches, char* err, int errlen) {
+               int* launches, char* err, int errlen, float* centroid_bounds) {
     *out_count = 0;
     float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
     int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
@@ -318,7 +318,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         TAKE(keys1, uint32_t, (size_t)n);
         TAKE(vals0, int, (size_t)n);
         TAKE(vals1, int, (size_t)n);
-        TAKE(hist, int, 256 * 256);
+        TAKE(hist, int, 256 * SORT_MAX_BLOCKS);
         TAKE(left, int, (size_t)n);
         TAKE(right, int, (size_t)n);
         TAKE(pint, int, (size_t)n);
@@ -387,6 +387,8 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         }
     }
     *out_count = total_nodes;
+    if (centroid_bounds)
+        for (int a = 0; a < 6; a++) centroid_bounds[a] = ord2f(hb[a]);
     return RT_OK;
 fail:
     return RT_ERR_CUDA;

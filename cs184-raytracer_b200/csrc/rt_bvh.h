@@ -35,7 +35,7 @@ struct DeviceArena {
 
 // scratch bytes build_lbvh takes from the arena for n primitives
 inline size_t lbvh_scratch_bytes(size_t n) {
-    return 4 * DeviceArena::padded(12 * n) + 10 * DeviceArena::padded(4 * n) + DeviceArena::padded(4 * 256 * 256) + 4096;
+    return 4 * DeviceArena::padded(12 * n) + 10 * DeviceArena::padded(4 * n) + DeviceArena::padded(4 * 256 * 4096 /* radix-sort histograms, SORT_MAX_BLOCKS */) + 4096;
 }
 
 // Builds one LBVH per primitive group over the n primitive codes in d_codes (device;
@@ -45,6 +45,7 @@ inline size_t lbvh_scratch_bytes(size_t n) {
 // primitives (the camera eye), folded into the box padding.  Returns RT_OK or RT_ERR_CUDA.
 int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code, int n, const int* group_sizes, int ngroups,
                float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes /* >= n + ngroups */,
-               size_t* out_count, int* launches, char* err, int errlen);
+               size_t* out_count, int* launches, char* err, int errlen,
+               float* centroid_bounds /* [6] or null: min xyz, max xyz of the primitive centroids */);
 
 }  // namespace rt

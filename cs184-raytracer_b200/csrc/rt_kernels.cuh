@@ -167,6 +167,50 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S
     flush_work<COUNT>(wc, ctr + CTR_NODES);
 }
 
+// ---- hit sorting (bounce levels >= 1) -----------------------------------------------------
+// Hits of reflected / refracted rays arrive in an order that has little to do with where they
+// are: ncu (round 1) shows 8 active lanes per instruction in the k_shadow launches of the
+// bounce levels against 18 on the primary level.  Sorting the hit records by a Morton code of
+// the hit point makes a warp 32 neighbouring origins again — for the shadow rays of this level
+// and, because k_shade spawns in hit order, for the next level's rays.
+struct SortGrid {
+    float lo[3];
+    float scale;      // cells per world unit (same on the three axes: cubic cells)
+    int bits;         // key bits (multiple of 8 for the radix passes)
+};
+__device__ __forceinline__ uint32_t spread_bits3(uint32_t v) {   // 10 bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void k_hit_keys(HitQ h, const unsigned long long* __restrict__ lc, SortGrid g, uint32_t* __restrict__ keys,
+                           int* __restrict__ vals) {
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (unsigned)lc[CTR_HITS]) return;
+    const float p[3] = {(float)h.fld(0, j), (float)h.fld(1, j), (float)h.fld(2, j)};
+    uint32_t q[3];
+    for (int a = 0; a < 3; a++) {
+        float u = (p[a] - g.lo[a]) * g.scale;
+        q[a] = (uint32_t)min(max((int)u, 0), 1023);
+    }
+    const uint32_t m = (spread_bits3(q[0]) << 2) | (spread_bits3(q[1]) << 1) | spread_bits3(q[2]);
+    keys[j] = m >> (30 - g.bits);         // the top `bits` bits: coarser cells, fewer radix passes
+    vals[j] = (int)j;
+}
+// dst[j] = src[order[j]]
+__global__ void k_permute_hits(HitQ src, HitQ dst, const unsigned long long* __restrict__ lc, const int* __restrict__ order) {
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (unsigned)lc[CTR_HITS]) return;
+    const unsigned s = (unsigned)order[j];
+#pragma unroll
+    for (int k = 0; k < 13; k++) dst.fld(k, j) = src.fld(k, s);
+    dst.pixel[j] = src.pixel[s];
+    dst.geom[j] = src.geom[s];
+    dst.meta[j] = src.meta[s];
+}
+
 // --intersection-only: pixel = 1/dist^2 on all channels (src/scene.cpp:69-70)
 __global__ void __launch_bounds__(RT_BLOCK) k_shade_io(HitQ h, const unsigned long long* ctr, double* fb,
                                                         unsigned long long* maxbits) {

@@ -10,7 +10,7 @@ namespace rt {
 
 #define SORT_THREADS 256
 #define SORT_WARPS (SORT_THREADS / 32)
-#define SORT_MAX_BLOCKS 256
+#define SORT_MAX_BLOCKS 4096
 
 __device__ __forceinline__ void sort_extent(int& n, int& chunk, int nblocks, const unsigned long long* n_dev) {
     if (n_dev) n = (int)*n_dev;
@@ -31,7 +31,7 @@ static __global__ void k_sort_hist(const uint32_t* __restrict__ keys, int n, con
     hist[threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
 }
 
-// exclusive scan of `count` ints (count <= 65536) by ONE block of 1024 threads
+// exclusive scan of `count` ints (<= 256 * SORT_MAX_BLOCKS) by ONE block of 1024 threads
 static __global__ void k_sort_scan(int* __restrict__ data, int count) {
     __shared__ int warp_sums[32];
     const int per = (count + 1023) / 1024;
