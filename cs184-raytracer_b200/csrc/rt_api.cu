@@ -562,6 +562,7 @@ struct RenderJob {
     bool brute, count, timed, overlap;
     int sort_bits;                 // 0: no hit sorting
     size_t sort_min_rays;          // levels with fewer rays are not worth the extra launches
+    int sort_first_level;          // 0: primary hits too (8x4-pixel blocks are coherent on screen, less so in space)
     int* ids_geom;
     int* ids_face;
     unsigned long long* maxbits;   // intersection-only
@@ -664,7 +665,7 @@ int process_level(RenderJob& J, int level, size_t n) {
         }
         CU(cudaMemsetAsync(lc, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
         int lrc;
-        const bool sorting = J.sort_bits > 0 && level >= 1 && (size_t)m >= J.sort_min_rays && !ids_only && !io;
+        const bool sorting = J.sort_bits > 0 && level >= J.sort_first_level && (size_t)m >= J.sort_min_rays && !ids_only && !io;
         HitQ ht = h;               // where k_trace appends
         if (sorting) {
             ht.f = ctx->hsf.p;
@@ -789,16 +790,17 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     J.timed = (p->flags & RT_FLAG_TIME_KERNELS) != 0;
     J.overlap = overlap;
     {   // Hit sorting (k_hit_keys): pays when divergence is expensive, i.e. on big LBVHs — measured on
-        // B200: 1M-triangle scene at 8K 160.8 -> 127.9 ms; bunny (5k faces) at 4K 13.2 -> 14.0 ms.
-        // RT_HIT_SORT_BITS = 0 (off), 8, 16 or 24 key bits; RT_HIT_SORT_MIN_PRIMS / _MIN_RAYS: thresholds.
+        // B200: 1M-triangle scene at 8K 160.6 -> 109.3 ms; bunny (5k faces) at 4K 13.2 -> 12.2 ms.
+        // RT_HIT_SORT_BITS = 0 (off), 8, 16 or 24 key bits; RT_HIT_SORT_MIN_PRIMS / _MIN_RAYS / _FIRST_LEVEL: thresholds.
         const char* sb = getenv("RT_HIT_SORT_BITS");
         const char* mp = getenv("RT_HIT_SORT_MIN_PRIMS");
         const char* mr = getenv("RT_HIT_SORT_MIN_RAYS");
         int bits = sb ? atoi(sb) : 24;
         bits = bits / 8 * 8;
-        if (bits > 24) bits = 24;
-        const long long min_prims = mp ? atoll(mp) : 65536;
-        J.sort_min_rays = mr ? (size_t)atoll(mr) : 65536;
+        if (bits > 32) bits = 32;          // 32: all 30 Morton bits (four radix passes)
+        const long long min_prims = mp ? atoll(mp) : 2;
+        J.sort_min_rays = mr ? (size_t)atoll(mr) : 262144;
+        J.sort_first_level = getenv("RT_HIT_SORT_FIRST_LEVEL") ? atoi(getenv("RT_HIT_SORT_FIRST_LEVEL")) : 0;
         J.sort_bits = (bits > 0 && ctx->sort_ok && ctx->S.num_bvh_prims >= min_prims && !J.brute && p->bounce_depth >= 1 &&
                        !ids_only && !p->intersection_only) ? bits : 0;
     }
@@ -809,7 +811,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
             CU(ctx->skeys[k].ensure(maxchunk));
             CU(ctx->svals[k].ensure(maxchunk));
         }
-        CU(ctx->shist.ensure((size_t)256 * SORT_MAX_BLOCKS));
+        CU(ctx->shist.ensure((size_t)256 * (SORT_MAX_BLOCKS + 1)));
     }
     ctx->hq_pending[0] = ctx->hq_pending[1] = false;
     ctx->evused = 0;

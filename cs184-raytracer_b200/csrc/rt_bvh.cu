@@ -318,7 +318,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         TAKE(keys1, uint32_t, (size_t)n);
         TAKE(vals0, int, (size_t)n);
         TAKE(vals1, int, (size_t)n);
-        TAKE(hist, int, 256 * SORT_MAX_BLOCKS);
+        TAKE(hist, int, 256 * (SORT_MAX_BLOCKS + 1));
         TAKE(left, int, (size_t)n);
         TAKE(right, int, (size_t)n);
         TAKE(pint, int, (size_t)n);

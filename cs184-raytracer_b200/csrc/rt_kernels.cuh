@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S
 // are: ncu (round 1) shows 8 active lanes per instruction in the k_shadow launches of the
 // bounce levels against 18 on the primary level.  Sorting the hit records by a Morton code of
 // the hit point makes a warp 32 neighbouring origins again — for the shadow rays of this level
-// and, because k_shade spawns in hit order, for the next level's rays.
+// and, because k_shade spawns in hit order, for the next level's rays.  It pays on the primary
+// level too (neighbours on screen are not always neighbours in space).
 struct SortGrid {
     float lo[3];
     float scale;      // cells per world unit (same on the three axes: cubic cells)
@@ -196,7 +197,7 @@ __global__ void k_hit_keys(HitQ h, const unsigned long long* __restrict__ lc, So
         q[a] = (uint32_t)min(max((int)u, 0), 1023);
     }
     const uint32_t m = (spread_bits3(q[0]) << 2) | (spread_bits3(q[1]) << 1) | spread_bits3(q[2]);
-    keys[j] = m >> (30 - g.bits);         // the top `bits` bits: coarser cells, fewer radix passes
+    keys[j] = g.bits < 30 ? m >> (30 - g.bits) : m;     // the top `bits` bits: coarser cells, fewer radix passes
     vals[j] = (int)j;
 }
 // dst[j] = src[order[j]]

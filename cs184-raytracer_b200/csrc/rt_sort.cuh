@@ -31,14 +31,18 @@ static __global__ void k_sort_hist(const uint32_t* __restrict__ keys, int n, con
     hist[threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
 }
 
-// exclusive scan of `count` ints (<= 256 * SORT_MAX_BLOCKS) by ONE block of 1024 threads
-static __global__ void k_sort_scan(int* __restrict__ data, int count) {
-    __shared__ int warp_sums[32];
-    const int per = (count + 1023) / 1024;
-    int begin = threadIdx.x * per, end = min(begin + per, count);
+// Offsets from the per-block histograms hist[digit][block]: block `d` of k_sort_rowscan turns
+// row d into its exclusive prefix over the blocks and records the row total; k_sort_digitscan
+// turns the 256 totals into the digits' base offsets.  (A single-block scan over all
+// 256 * nblocks counters took 0.58 ms per radix pass at 4096 blocks — most of the sort.)
+static __global__ void k_sort_rowscan(int* __restrict__ hist, int nblocks, int* __restrict__ totals) {
+    __shared__ int warp_sums[SORT_WARPS];
+    int* row = hist + (size_t)blockIdx.x * nblocks;
+    const int per = (nblocks + SORT_THREADS - 1) / SORT_THREADS;
+    const int begin = min((int)threadIdx.x * per, nblocks), end = min(begin + per, nblocks);
     int sum = 0;
-    for (int i = begin; i < end; i++) sum += data[i];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = begin; i < end; i++) sum += row[i];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
         int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -46,34 +50,45 @@ static __global__ void k_sort_scan(int* __restrict__ data, int count) {
     }
     if (lane == 31) warp_sums[w] = incl;
     __syncthreads();
-    if (w == 0) {
-        int ws = warp_sums[lane];
-        int wi = ws;
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
-        }
-        warp_sums[lane] = wi - ws;
+    int wbase = 0, total = 0;
+    for (int k = 0; k < SORT_WARPS; k++) {
+        if (k < w) wbase += warp_sums[k];
+        total += warp_sums[k];
     }
-    __syncthreads();
-    int run = warp_sums[w] + incl - sum;
+    int run = wbase + incl - sum;
     for (int i = begin; i < end; i++) {
-        int v = data[i];
-        data[i] = run;
+        int v = row[i];
+        row[i] = run;
         run += v;
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+// exclusive scan of the 256 digit totals, in place, by one block of 256 threads
+static __global__ void k_sort_digitscan(int* __restrict__ totals) {
+    __shared__ int sh[256];
+    const int t = threadIdx.x;
+    const int v = totals[t];
+    sh[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        int add = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += add;
+        __syncthreads();
+    }
+    totals[t] = sh[t] - v;
 }
 
 static __global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
                                       uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int n,
                                       const unsigned long long* n_dev, int shift, int nblocks,
-                                      const int* __restrict__ offsets) {
+                                      const int* __restrict__ offsets, const int* __restrict__ digit_base) {
     __shared__ int base[256];
     __shared__ int warp_cnt[SORT_WARPS][256];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int chunk;
     sort_extent(n, chunk, nblocks, n_dev);
-    base[tid] = offsets[tid * nblocks + blockIdx.x];
+    base[tid] = offsets[tid * nblocks + blockIdx.x] + digit_base[tid];
     for (int k = 0; k < SORT_WARPS; k++) warp_cnt[k][tid] = 0;
     __syncthreads();
     int begin = blockIdx.x * chunk, end = min(begin + chunk, n);
@@ -107,7 +122,7 @@ static __global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, cons
 
 // Sorts by the low `bits` (multiple of 8) key bits.  n_max sizes the grid; the real count is
 // n_max, or *n_dev when n_dev != nullptr.  On return kin/vin point at the sorted data (the
-// pointers are swapped once per pass).  hist: 256 * SORT_MAX_BLOCKS ints of scratch.
+// pointers are swapped once per pass).  hist: 256 * (SORT_MAX_BLOCKS + 1) ints of scratch.
 static inline void sort_pairs(cudaStream_t stream, uint32_t*& kin, uint32_t*& kout, int*& vin, int*& vout, int* hist,
                               int n_max, const unsigned long long* n_dev, int bits, int* launches) {
     int sblocks = (n_max + 4095) / 4096;
@@ -115,9 +130,11 @@ static inline void sort_pairs(cudaStream_t stream, uint32_t*& kin, uint32_t*& ko
     if (sblocks < 1) sblocks = 1;
     for (int shift = 0; shift < bits; shift += 8) {
         k_sort_hist<<<sblocks, SORT_THREADS, 0, stream>>>(kin, n_max, n_dev, shift, sblocks, hist);
-        k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256 * sblocks);
-        k_sort_scatter<<<sblocks, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n_max, n_dev, shift, sblocks, hist);
-        if (launches) (*launches) += 3;
+        int* totals = hist + (size_t)256 * SORT_MAX_BLOCKS;
+        k_sort_rowscan<<<256, SORT_THREADS, 0, stream>>>(hist, sblocks, totals);
+        k_sort_digitscan<<<1, 256, 0, stream>>>(totals);
+        k_sort_scatter<<<sblocks, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n_max, n_dev, shift, sblocks, hist, totals);
+        if (launches) (*launches) += 4;
         uint32_t* tk = kin; kin = kout; kout = tk;
         int* tv = vin; vin = vout; vout = tv;
     }
