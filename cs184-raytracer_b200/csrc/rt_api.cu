@@ -790,12 +790,12 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     J.timed = (p->flags & RT_FLAG_TIME_KERNELS) != 0;
     J.overlap = overlap;
     {   // Hit sorting (k_hit_keys): pays when divergence is expensive, i.e. on big LBVHs — measured on
-        // B200: 1M-triangle scene at 8K 160.6 -> 109.3 ms; bunny (5k faces) at 4K 13.2 -> 12.2 ms.
+        // B200: 1M-triangle scene at 8K 160.6 -> 107.2 ms (30-bit keys; 109.0 with 24); bunny (5k faces) at 4K 13.2 -> 12.2 ms.
         // RT_HIT_SORT_BITS = 0 (off), 8, 16 or 24 key bits; RT_HIT_SORT_MIN_PRIMS / _MIN_RAYS / _FIRST_LEVEL: thresholds.
         const char* sb = getenv("RT_HIT_SORT_BITS");
         const char* mp = getenv("RT_HIT_SORT_MIN_PRIMS");
         const char* mr = getenv("RT_HIT_SORT_MIN_RAYS");
-        int bits = sb ? atoi(sb) : 24;
+        int bits = sb ? atoi(sb) : 32;
         bits = bits / 8 * 8;
         if (bits > 32) bits = 32;          // 32: all 30 Morton bits (four radix passes)
         const long long min_prims = mp ? atoll(mp) : 2;
