@@ -63,7 +63,7 @@ class rt_scene(C.Structure):
 class rt_params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bounce_depth", C.c_int32),
                 ("intersection_only", C.c_int32), ("tile_rank", C.c_int32), ("tile_world", C.c_int32),
-                ("flags", C.c_uint32), ("reserved_", C.c_int32)]
+                ("flags", C.c_uint32), ("samples", C.c_int32)]
 
 
 class rt_stats(C.Structure):
@@ -240,8 +240,10 @@ def flat_arrays(flat) -> dict:
     }
 
 
-def make_params(width, height, bounce_depth=10, intersection_only=False, tile_rank=0, tile_world=1, flags=0) -> rt_params:
+def make_params(width, height, bounce_depth=10, intersection_only=False, tile_rank=0, tile_world=1, flags=0,
+                samples=0) -> rt_params:
     p = rt_params()
+    p.samples = int(samples)
     p.width, p.height, p.bounce_depth = int(width), int(height), int(bounce_depth)
     p.intersection_only = int(bool(intersection_only))
     p.tile_rank, p.tile_world, p.flags = int(tile_rank), int(tile_world), int(flags)
@@ -270,8 +272,8 @@ class Renderer:
         self._scene_keepalive = scene
         self._check(self.lib.rt_scene_upload(self._h, C.cast(flat, C.c_void_p)), "rt_scene_upload")
 
-    def render(self, width, height, bounce_depth=10, intersection_only=False, flags=0) -> np.ndarray:
-        p = make_params(width, height, bounce_depth, intersection_only, flags=flags)
+    def render(self, width, height, bounce_depth=10, intersection_only=False, flags=0, samples=0) -> np.ndarray:
+        p = make_params(width, height, bounce_depth, intersection_only, flags=flags, samples=samples)
         out = np.empty((height, width, 3), dtype=np.float64)
         self._check(self.lib.rt_render(self._h, C.byref(p), _ptr(out), None, None), "rt_render")
         return out

@@ -748,6 +748,8 @@ int check_params(rt_context* ctx, const rt_params* p) {
     if (p->bounce_depth < 0 || p->bounce_depth > 255) return fail(RT_ERR_INVALID, "bounce_depth must be in [0,255]");
     if (p->tile_world < 1 || p->tile_rank < 0 || p->tile_rank >= p->tile_world)
         return fail(RT_ERR_INVALID, "tile_rank/tile_world out of range");
+    if (p->samples < 0 || p->samples > RT_MAX_SAMPLES) return fail(RT_ERR_INVALID, "samples must be in [0,%d]", RT_MAX_SAMPLES);
+    if (p->samples > 1 && p->intersection_only) return fail(RT_ERR_INVALID, "supersampling is not defined for intersection_only");
     return RT_OK;
 }
 
@@ -771,7 +773,8 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         // (measured on B200, 8K synthetic frame: k_trace 52.5 ms with 8 Mi-slot queues, 44.7 ms
         // with 64 Mi).  64 Mi slots = 5.1 GB per bounce level, 3.7 GB of hit queue.
         const size_t unit = 2 * RT_TILE_PIXELS, lo = (size_t)1 << 20, hi = (size_t)64 << 20;
-        size_t want = (2 * (size_t)nslots + unit - 1) / unit * unit;
+        const size_t ss = p->samples > 1 ? (size_t)p->samples * p->samples : 1;
+        size_t want = (2 * (size_t)nslots * ss + unit - 1) / unit * unit;
         ctx->cap = std::min(std::max(want, lo), hi);
     }
     const size_t maxchunk = ctx->cap / 2;
@@ -843,18 +846,23 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     FrameInfo F;
     F.width = p->width; F.height = p->height; F.tiles_x = T.tiles_x; F.tiles_y = T.tiles_y; F.tile_ids = ctx->tile_ids.p;
     const long long total_px = (long long)p->width * p->height;
-    for (long long first = 0; first < nslots; first += (long long)maxchunk) {
-        const int n = (int)std::min<long long>((long long)maxchunk, nslots - first);
+    const int sub = p->samples > 1 ? p->samples : 1;
+    if (sub > 1 && ids_only) return fail(RT_ERR_INVALID, "primary ids are per pixel: render them with samples <= 1");
+    // slots per batch: a batch's primary rays (sub^2 per slot) must fit half a queue
+    const long long slots_per_batch = std::max<long long>((long long)maxchunk / (sub * sub), 1);
+    for (long long first = 0; first < nslots; first += slots_per_batch) {
+        const long long nslot_batch = std::min<long long>(slots_per_batch, nslots - first);
+        const int n = (int)(nslot_batch * sub * sub);
         {
             LaunchTimer lt(J, 3);
-            k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0));
+            k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0), sub);
         }
         J.launches++;
         LAUNCHED("k_raygen", st);
         rc = process_level(J, 0, (size_t)n);
         if (rc != RT_OK) return rc;
         if (cb) {
-            long long done = std::min<long long>((first + n) * (long long)p->tile_world, total_px - 1);
+            long long done = std::min<long long>((first + nslot_batch) * (long long)p->tile_world, total_px - 1);
             cb((int)done, (int)total_px, user);
         }
     }
@@ -885,7 +893,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         int w = std::min(RT_TILE_W, p->width - tx * RT_TILE_W), hgt = std::min(RT_TILE_H, p->height - ty * RT_TILE_H);
         prim += (long long)w * hgt;
     }
-    stats.rays_primary = (uint64_t)prim;
+    stats.rays_primary = (uint64_t)prim * (uint64_t)(sub * sub);
     for (int l = 0; l < used_levels; l++) {
         const unsigned long long* c = ctx->h_ctr + (size_t)l * CTR_COUNT;
         stats.degenerate_rays += c[CTR_DEGENERATE];

@@ -104,14 +104,24 @@ __device__ __forceinline__ void flush_work(const WorkCounters& wc, unsigned long
     }
 }
 
+// sub > 1: supersampling — queue entry i is sample (i % sub^2) of slot first_slot + i / sub^2; its ray goes
+// through the centre of cell (si, sj) of the sub x sub grid inside the pixel and carries weight 1/sub^2.
 __global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long long first_slot, int n, int depth,
-                                                      RayQ q) {
+                                                      RayQ q, int sub) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    long long slot = first_slot + i;
+    const int ss = sub * sub;
+    long long slot = first_slot + (sub > 1 ? i / ss : i);
     int px, py;
     if (!slot_to_pixel(F, slot, px, py)) { q.pixel[i] = -1; return; }
     double rowFrac = (py + 0.5) / F.height, colFrac = (px + 0.5) / F.width;
+    double w = 1.0;
+    if (sub > 1) {
+        const int k = i % ss, si = k % sub, sj = k / sub;
+        rowFrac = (py + (sj + 0.5) / sub) / F.height;
+        colFrac = (px + (si + 0.5) / sub) / F.width;
+        w = 1.0 / ss;
+    }
     const DCamera& c = S.cam;
     d3 LR = mk3(c.lr[0], c.lr[1], c.lr[2]), UR = mk3(c.ur[0], c.ur[1], c.ur[2]);
     d3 LL = mk3(c.ll[0], c.ll[1], c.ll[2]), UL = mk3(c.ul[0], c.ul[1], c.ul[2]);
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long
     d3 d = ok ? ray_normalize(raw) : raw;
     q.fld(0, i) = E.x; q.fld(1, i) = E.y; q.fld(2, i) = E.z;
     q.fld(3, i) = d.x; q.fld(4, i) = d.y; q.fld(5, i) = d.z;
-    q.fld(6, i) = 1.0; q.fld(7, i) = 1.0; q.fld(8, i) = 1.0;
+    q.fld(6, i) = w; q.fld(7, i) = w; q.fld(8, i) = w;
     q.pixel[i] = ok ? (int)slot : -1;
     q.meta[i] = depth;
 }

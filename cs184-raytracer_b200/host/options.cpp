@@ -13,7 +13,7 @@ namespace as2 {
 Options programOptions;
 
 namespace {
-enum { kHelp = 1000, kBounceDepth, kIntersectionOnly, kBruteForce };
+enum { kHelp = 1000, kBounceDepth, kIntersectionOnly, kBruteForce, kSamples };
 const struct option kLongOptions[] = {
     {"help", no_argument, nullptr, kHelp},
     {"output", required_argument, nullptr, 'o'},
@@ -23,6 +23,7 @@ const struct option kLongOptions[] = {
     {"bdepth", required_argument, nullptr, kBounceDepth},
     {"intersection-only", no_argument, nullptr, kIntersectionOnly},
     {"brute-force", no_argument, nullptr, kBruteForce},
+    {"aa", required_argument, nullptr, kSamples},
     {nullptr, 0, nullptr, 0},
 };
 
@@ -64,6 +65,10 @@ bool Options::parseCommandLine(int argc, char* argv[]) {
                 if (!toInt(optarg, bounceDepth_)) return fail("Bounce depth is invalid.");
                 if (bounceDepth_ < 0) return fail("Bounce depth must be non-negative.");
                 break;
+            case kSamples:
+                if (!toInt(optarg, samples_)) return fail("Sample count is invalid.");
+                if (samples_ < 1 || samples_ > 16) return fail("Sample count must be between 1 and 16.");
+                break;
             case kHelp:
             case '?':
             default:
@@ -74,6 +79,7 @@ bool Options::parseCommandLine(int argc, char* argv[]) {
     for (; optind < argc; optind++) inputFilenames_.push_back(argv[optind]);
     if (inputFilenames_.empty()) return fail("At least one input file must be specified.");
     if (outputFilename_.empty()) return fail("An output file must be specified.");
+    if (samples_ > 1 && intersectionOnly_) return fail("--aa cannot be combined with --intersection-only.");
     return true;
 }
 

@@ -2,7 +2,8 @@
 // (src/options.h:5-30, src/options.cpp:7-90): -t/--threads, -w/--width, -h/--height
 // (-h is HEIGHT, not help), -o/--output, --bdepth, --intersection-only, --help,
 // positional .rti files; one global instance `programOptions` that the render path
-// reads, exactly as src/scene.cpp:31,39,50,69 do.  Extra (ours): --gpus N.
+// reads, exactly as src/scene.cpp:31,39,50,69 do.  Extra (ours): --brute-force, and --aa N
+// (N x N supersampling, the reference's stated next feature, TODO:2).
 #pragma once
 #include <string>
 #include <vector>
@@ -22,6 +23,7 @@ public:
     int bounceDepth_ = 10;
     bool intersectionOnly_ = false;
     bool bruteForce_ = false;      // --brute-force: debug aid, skips the LBVH
+    int samples_ = 1;              // --aa N: N x N rays per pixel, averaged (1 = the reference's single centre ray)
 };
 
 extern Options programOptions;

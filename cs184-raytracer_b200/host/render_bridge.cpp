@@ -37,6 +37,7 @@ rt_params paramsFromOptions(int width, int height) {
     p.tile_rank = 0;
     p.tile_world = 1;
     p.flags = programOptions.bruteForce_ ? RT_FLAG_BRUTE_FORCE : 0u;
+    p.samples = programOptions.samples_;
     return p;
 }
 }  // namespace

@@ -135,8 +135,12 @@ typedef struct rt_params {
     int32_t  tile_rank;          /* this process renders tiles with tile % tile_world == tile_rank */
     int32_t  tile_world;         /* number of cooperating processes/GPUs (>=1)       */
     uint32_t flags;              /* RT_FLAG_*                                        */
-    int32_t  reserved_;
+    int32_t  samples;            /* supersampling (the reference's stated next feature, TODO:2): 0 or 1 =
+                                    one ray through the pixel centre (src/scene.cpp:28-29); n > 1 = n x n
+                                    rays through the centres of an n x n grid inside the pixel, averaged.
+                                    n <= RT_MAX_SAMPLES; not with intersection_only / rt_primary_ids      */
 } rt_params;
+#define RT_MAX_SAMPLES 16
 
 /* Progress callback == Scene::ProgressHandler (src/scene.h:12).  Invoked on the
  * calling thread only, monotone, and once at the end with (total,total)

@@ -287,9 +287,15 @@ static void trace_ray(const rt_scene* s, const rt_params* p, v3 o, v3 d, int dep
 }
 
 /* Camera::calculateViewingRay (src/rtbase.h:74-84) at pixel (r,c) (src/scene.cpp:26-30) */
-static void camera_ray(const rt_scene* s, int width, int height, int r, int c, v3* o, v3* d) {
+/* sub > 1: the ray through the centre of cell (si, sj) of a sub x sub grid inside the pixel
+ * (supersampling, the extension of src/scene.cpp:28-29 described at rt_params.samples). */
+static void camera_ray_sub(const rt_scene* s, int width, int height, int r, int c, int sub, int si, int sj, v3* o, v3* d) {
     const rt_camera* cam = &s->camera;
     double rowFrac = (r + 0.5) / height, colFrac = (c + 0.5) / width;
+    if (sub > 1) {
+        rowFrac = (r + (sj + 0.5) / sub) / height;
+        colFrac = (c + (si + 0.5) / sub) / width;
+    }
     v3 LR = ld3(cam->lr), UR = ld3(cam->ur), LL = ld3(cam->ll), UL = ld3(cam->ul), E = ld3(cam->eye);
     v3 right = vadd(vscale(rowFrac, LR), vscale(1.0 - rowFrac, UR));
     v3 left = vadd(vscale(rowFrac, LL), vscale(1.0 - rowFrac, UL));
@@ -297,6 +303,9 @@ static void camera_ray(const rt_scene* s, int width, int height, int r, int c, v
     v3 raw = vsub(ip, E);
     *o = E;
     *d = vdiv(raw, norm4(raw));
+}
+static void camera_ray(const rt_scene* s, int width, int height, int r, int c, v3* o, v3* d) {
+    camera_ray_sub(s, width, height, r, c, 1, 0, 0, o, d);
 }
 
 /* ---- public (test-only) API --------------------------------------------- */
@@ -319,6 +328,20 @@ static void* worker(void* arg) {
         for (int64_t i = start; i < end; i++) {
             int r = (int)(i / W), c = (int)(i % W);
             v3 o, d;
+            const int sub = j->p->samples > 1 ? j->p->samples : 1;
+            if (sub > 1) {          /* mean of the sub x sub sample colours */
+                double acc[3] = {0, 0, 0}, col[3];
+                for (int sj = 0; sj < sub; sj++)
+                    for (int si = 0; si < sub; si++) {
+                        camera_ray_sub(j->s, W, H, r, c, sub, si, sj, &o, &d);
+                        j->cnt.primary++;
+                        col[0] = col[1] = col[2] = 0.0;
+                        trace_ray(j->s, j->p, o, d, j->p->bounce_depth, 0, &j->cnt, col);
+                        for (int k = 0; k < 3; k++) acc[k] += col[k] * (1.0 / (sub * sub));
+                    }
+                for (int k = 0; k < 3; k++) j->rgb[3 * i + k] = acc[k];
+                continue;
+            }
             camera_ray(j->s, W, H, r, c, &o, &d);
             j->cnt.primary++;
             trace_ray(j->s, j->p, o, d, j->p->bounce_depth, 0, &j->cnt, j->rgb + 3 * i);

@@ -59,9 +59,9 @@ class Oracle:
     def __init__(self):
         self.lib = C.CDLL(str(ORACLE_DIR / "liboracle.so"))
 
-    def render(self, flat, width, height, depth=10, intersection_only=False, threads=8, ids=True):
+    def render(self, flat, width, height, depth=10, intersection_only=False, threads=8, ids=True, samples=0):
         pkg = load_package()
-        p = pkg.make_params(width, height, depth, intersection_only)
+        p = pkg.make_params(width, height, depth, intersection_only, samples=samples)
         rgb = np.zeros((height, width, 3))
         geom = np.zeros((height, width), np.int32) if ids else None
         face = np.zeros((height, width), np.int32) if ids else None

@@ -7,6 +7,8 @@ within 1e-9 absolute (summation order of the iterative bounce loop and CUDA's po
 from the recursion in the last ulps); 8-bit images within 1/255 on >= 99.9 % of pixels and no
 pixel off by more than 4/255 (BASELINE.json north_star).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -319,3 +321,54 @@ def test_hit_sorting_and_overlap_do_not_change_the_result(pkg, scenes, monkeypat
         assert np.array_equal(g, fx["geom"])
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("name,samples", [("input-02", 2), ("input-05", 3), ("refraction3", 2), ("bunny4", 4)])
+def test_supersampling_matches_the_oracle(pkg, gpu_renderer, oracle, scenes, name, samples):
+    """SURVEY section 8 f-4 (the reference's TODO:2): n x n rays per pixel through the cell centres, averaged.
+    samples = 1 is the reference's pixel-centre ray (all other tests); n > 1 is checked against the oracle's
+    restatement of the same rule: ray counts exact, frame within the FP64 tolerance."""
+    sc = scenes(name)
+    gpu_renderer.upload(sc)
+    w, h, depth = 61, 47, 5
+    rgb = gpu_renderer.render(w, h, depth, samples=samples)
+    st = gpu_renderer.stats()
+    o_rgb, _, _, counts = oracle.render(sc.flat, w, h, depth, ids=False, samples=samples)
+    assert [st["rays_primary"], st["rays_shadow"], st["rays_secondary"]] == counts[:3]
+    assert st["rays_primary"] == w * h * samples * samples
+    assert np.abs(rgb - o_rgb).max() <= FP64_TOL
+    one = gpu_renderer.render(w, h, depth)
+    assert np.abs(rgb - one).max() > 1e-3           # it does change edges ...
+    assert np.abs(rgb.mean() - one.mean()) < 0.02    # ... and not the overall picture
+
+
+def test_supersampling_argument_checks(pkg, gpu_renderer, scenes):
+    gpu_renderer.upload(scenes("input-01"))
+    with pytest.raises(pkg.RtError):
+        gpu_renderer.render(8, 8, 2, samples=17)
+    with pytest.raises(pkg.RtError):
+        gpu_renderer.render(8, 8, 2, intersection_only=True, samples=2)
+    a = gpu_renderer.render(8, 8, 2, samples=1)
+    b = gpu_renderer.render(8, 8, 2, samples=0)
+    assert np.abs(a - b).max() <= FP64_TOL      # (atomic accumulation order: equal up to 1e-16)
+
+
+def test_as2_cli_supersampling_and_f64_frame(pkg, oracle, scenes, tmp_path, monkeypatch):
+    """--aa N through the executable (PNG == quantised oracle frame), and the reference-style double-frame path
+    of main (AS2_F64_FRAME) writes the same bytes as the default device-quantised path."""
+    import subprocess
+    from conftest import PKG_DIR
+    exe, rti = str(PKG_DIR / "bin" / "as2"), str(scene_path("inputs/input-05.rti"))
+    a, b, c = tmp_path / "a.png", tmp_path / "b.png", tmp_path / "c.png"
+    for out, extra, env in ((a, ["--aa", "3"], {}), (b, [], {}), (c, [], {"AS2_F64_FRAME": "1"})):
+        e = dict(os.environ, **env)
+        proc = subprocess.run([exe, rti, "-o", str(out), "-w", "90", "-h", "70", "--bdepth", "4"] + extra, capture_output=True,
+                              text=True, env=e)
+        assert proc.returncode == 0, proc.stderr
+    sc = scenes("input-05")
+    o3, _, _, _ = oracle.render(sc.flat, 90, 70, 4, ids=False, samples=3)
+    o1, _, _, _ = oracle.render(sc.flat, 90, 70, 4, ids=False)
+    d3 = np.abs(decode_png(a).astype(np.int16) - quantize(o3).astype(np.int16))
+    assert int(d3.max()) <= 1 and float((d3 == 0).mean()) > 0.999       # truncating quantiser at 1e-16 differences
+    assert np.array_equal(decode_png(b), quantize(o1))
+    assert np.array_equal(decode_png(b), decode_png(c))

@@ -127,6 +127,9 @@ CLI_ERRORS = [
     (["-w", "-3", "-o", "o.png", "x.rti"], "Error: Width and/or height must be positive."),
     (["-h", "abc", "-o", "o.png", "x.rti"], "Error: Width and/or height is invalid."),
     (["--bdepth", "-1", "-o", "o.png", "x.rti"], "Error: Bounce depth must be non-negative."),
+    (["--aa", "0", "-o", "o.png", "x.rti"], "Error: Sample count must be between 1 and 16."),
+    (["--aa", "q", "-o", "o.png", "x.rti"], "Error: Sample count is invalid."),
+    (["--aa", "2", "--intersection-only", "-o", "o.png", "x.rti"], "Error: --aa cannot be combined with --intersection-only."),
     (["--help"], "Usage: "),
     (["-o", "/nonexistent-dir/o.png", "x.rti"], "Error: Output file is not writable."),
 ]

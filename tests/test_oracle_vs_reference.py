@@ -82,3 +82,36 @@ def test_oracle_reproduces_golden_images(pkg, oracle, n):
     rgb, _, _, _ = oracle.render(sc.flat, size, size, 10, ids=False)
     gold = decode_png(GOLDEN / "outputs" / f"image-{n}.png")
     assert np.array_equal(quantize(rgb), gold)
+
+
+@pytest.mark.parametrize("name,sub", [("inputs/input-05.rti", 2), ("inputs/input-06.rti", 3), ("excess_inputs/refraction3.rti", 2)])
+def test_oracle_supersampling_is_the_mean_of_reference_traces(pkg, oracle, reference, name, sub):
+    """SURVEY section 8 f-4.  rt_params.samples = n is defined as the mean of the reference's traceRay over the
+    centres of an n x n grid inside each pixel.  The unmodified reference traces the sample rays (built here
+    in numpy with Camera::calculateViewingRay's blend, src/rtbase.h:74-84); the oracle's loop must agree.
+    (ref_trace_rays re-normalises the direction through the Ray constructor, hence 1e-12 and not 0.)"""
+    sc = pkg.HostScene.load(scene_path(name))
+    h = reference.load(scene_path(name))
+    w, hh, depth = 23, 17, 4
+    cam = pkg.flat_arrays(sc.flat)["camera"]
+    E, LL, LR, UL, UR = (cam[3 * k:3 * k + 3] for k in range(5))
+    orgs, dirs = [], []
+    for r in range(hh):
+        for c in range(w):
+            for sj in range(sub):
+                for si in range(sub):
+                    rowf = (r + (sj + 0.5) / sub) / hh
+                    colf = (c + (si + 0.5) / sub) / w
+                    right = rowf * LR + (1.0 - rowf) * UR
+                    left = rowf * LL + (1.0 - rowf) * UL
+                    raw = (colf * right + (1.0 - colf) * left) - E
+                    orgs.append(E)
+                    dirs.append(raw)
+    cols = reference.trace_rays(h, np.array(orgs), np.array(dirs), depth)
+    mean = cols.reshape(hh, w, sub * sub, 3).sum(axis=2) / (sub * sub)
+    rgb, _, _, counts = oracle.render(sc.flat, w, hh, depth, ids=False, samples=sub)
+    assert counts[0] == w * hh * sub * sub
+    assert np.abs(rgb - mean).max() <= 1e-12
+    one, _, _, c1 = oracle.render(sc.flat, w, hh, depth, ids=False, samples=1)
+    zero, _, _, c0 = oracle.render(sc.flat, w, hh, depth, ids=False, samples=0)
+    assert np.array_equal(one, zero) and c1 == c0 and c1[0] == w * hh
