@@ -27,7 +27,7 @@ RT_FLAG_BRUTE_FORCE = 1
 RT_FLAG_COUNT_WORK = 2
 RT_FLAG_TIME_KERNELS = 4
 RT_FLAG_SERIAL = 8
-RT_TILE_PIXELS = 32 * 32
+RT_TILE_PIXELS = int(os.environ.get("RT_B200_TILE", "32")) ** 2    # must match the library build (include/rt_b200.h)
 
 
 class rt_material(C.Structure):

@@ -1063,7 +1063,7 @@ int rt_primary_ids(rt_context* ctx, const rt_params* p, int32_t* geom, int32_t* 
         int gt = T.ids[lt], tx = gt % T.tiles_x, ty = gt / T.tiles_x;
         for (int j = 0; j < RT_TILE_PIXELS; j++) {
             int w = j >> 5, l = j & 31;
-            int px = tx * RT_TILE_W + (w & 3) * 8 + (l & 7), py = ty * RT_TILE_H + (w >> 2) * 4 + (l >> 3);
+            int px = tx * RT_TILE_W + (w % (RT_TILE_W / 8)) * 8 + (l & 7), py = ty * RT_TILE_H + (w / (RT_TILE_W / 8)) * 4 + (l >> 3);
             if (px >= p->width || py >= p->height) continue;
             size_t dst = (size_t)py * p->width + px, src = lt * RT_TILE_PIXELS + j;
             geom[dst] = hg[src];

@@ -20,17 +20,6 @@
 
 #include "rt_b200.h"
 
-// build-time tunables (A/B'd on B200 with tools/ab.sh)
-#ifndef RT_PREFETCH_PUSH
-#define RT_PREFETCH_PUSH 0
-#endif
-#ifndef RT_DUMMY_LOAD
-#define RT_DUMMY_LOAD 0
-#endif
-#ifndef RT_NOINLINE_PRIM
-#define RT_NOINLINE_PRIM 0
-#endif
-
 namespace rt {
 
 struct d3 {
@@ -323,13 +312,8 @@ __device__ __forceinline__ bool sphere_certainly_missed(float4 bs, d3 o, d3 d) {
 }
 
 // Dispatch one prim code.  Returns true only for ANYHIT occlusion.
-#if RT_NOINLINE_PRIM
-#define RT_PRIM_INLINE __noinline__
-#else
-#define RT_PRIM_INLINE __forceinline__
-#endif
 template <bool ANYHIT, bool COUNT>
-__device__ RT_PRIM_INLINE bool test_prim(const DScene& S, int code, d3 o, d3 d, bool reverse, double limit,
+__device__ __forceinline__ bool test_prim(const DScene& S, int code, d3 o, d3 d, bool reverse, double limit,
                                           ObjRay& R, Best& best, WorkCounters& wc) {
     const int kind = code >> PRIM_KIND_SHIFT, idx = code & PRIM_INDEX_MASK;
     if (kind == PRIM_SPHERE) {
@@ -515,13 +499,7 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
         const float4* pnz = reinterpret_cast<const float4*>(nb + (off + fr.nz));
         const float4 nx = __ldg(pnx), ny = __ldg(pny), nz = __ldg(pnz);
         const float4 fx = __ldg(flip64(pnx)), fy = __ldg(flip64(pny)), fz = __ldg(flip64(pnz));
-        int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
-#if RT_DUMMY_LOAD
-        {   // experiment: one more 16-byte fetch per node visit (is the LSU data path the limiter?)
-            const int4 pd = __ldg(reinterpret_cast<const int4*>(nb + off + 112));
-            if (pd.x == 0x12345678) ref.x = pd.y;
-        }
-#endif
+        const int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
         if (COUNT) wc.nodes += 4;
         float t0, t1, t2, t3;
         bool h0, h1, h2, h3;

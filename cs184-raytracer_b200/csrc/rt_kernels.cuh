@@ -69,7 +69,7 @@ __device__ __forceinline__ bool slot_to_pixel(const FrameInfo& F, long long slot
     int gt = __ldg(F.tile_ids + lt);
     int tx = gt % F.tiles_x, ty = gt / F.tiles_x;
     int w = j >> 5, l = j & 31;                     // one warp = an 8x4 pixel block
-    int x = (w & 3) * 8 + (l & 7), y = (w >> 2) * 4 + (l >> 3);
+    int x = (w % (RT_TILE_W / 8)) * 8 + (l & 7), y = (w / (RT_TILE_W / 8)) * 4 + (l >> 3);
     px = tx * RT_TILE_W + x;
     py = ty * RT_TILE_H + y;
     return px < F.width && py < F.height;
@@ -435,7 +435,7 @@ __global__ void k_unpack(int width, int height, int tiles_x, int world, long lon
     int first_tx = ((rank - ty) % world + world) % world;
     long long lt = rank_row_start[rank * (tiles_y + 1) + ty] + (tx - first_tx) / world;
     int x = px % RT_TILE_W, y = py % RT_TILE_H;
-    int w = (y / 4) * 4 + (x / 8), l = (y % 4) * 8 + (x % 8);
+    int w = (y / 4) * (RT_TILE_W / 8) + (x / 8), l = (y % 4) * 8 + (x % 8);
     long long slot = ((long long)rank * max_tiles + lt) * RT_TILE_PIXELS + w * 32 + l;
     for (int k = 0; k < 3; k++) frame[i * 3 + k] = packed[slot * 3 + k];
 }

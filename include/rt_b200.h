@@ -201,8 +201,12 @@ int  rt_render_rgb8(rt_context* ctx, const rt_params* p, uint8_t* rgb8,
  * this rank's packed tiles (rt_tile_count()*RT_TILE_PIXELS pixels), to be
  * gathered by the caller (NCCL) and unpacked with rt_unpack_tiles*.
  * stream: a cudaStream_t passed as void* (0 = legacy default stream). */
+#ifndef RT_TILE_W
 #define RT_TILE_W      32
-#define RT_TILE_H      32
+#endif
+#ifndef RT_TILE_H
+#define RT_TILE_H      RT_TILE_W
+#endif
 #define RT_TILE_PIXELS (RT_TILE_W * RT_TILE_H)
 int     rt_render_device(rt_context* ctx, const rt_params* p, double* d_out, void* stream);
 int     rt_render_device_rgb8(rt_context* ctx, const rt_params* p, uint8_t* d_out, void* stream);
