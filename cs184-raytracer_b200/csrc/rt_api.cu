@@ -677,6 +677,7 @@ int process_level(RenderJob& J, int level, size_t n) {
         else lrc = J.count ? launch_trace<false, true>(J, q, off, m, ht, lc) : launch_trace<false, false>(J, q, off, m, ht, lc);
         if (lrc != RT_OK) return lrc;
         if (ids_only) continue;
+        const int* sorted_order = nullptr;
         if (sorting) {
             LaunchTimer lt(J, 3);
             const unsigned sb = (unsigned)((m + 255) / 256);
@@ -687,8 +688,8 @@ int process_level(RenderJob& J, int level, size_t n) {
             k_hit_keys<<<sb, 256, 0, J.st>>>(ht, lc, g, kin, vin);
             int nl = 0;
             sort_pairs(J.st, kin, kout, vin, vout, ctx->shist.p, m, lc + CTR_HITS, J.sort_bits, &nl);
-            k_permute_hits<<<sb, 256, 0, J.st>>>(ht, h, lc, vin);
-            J.launches += 2 + (uint64_t)nl;
+            sorted_order = vin;                 // k_shade gathers through it and writes the sorted queue
+            J.launches += 1 + (uint64_t)nl;
             LAUNCHED("hit sort", J.st);
         }
         const unsigned blocks = (unsigned)((m + RT_BLOCK - 1) / RT_BLOCK);
@@ -708,7 +709,7 @@ int process_level(RenderJob& J, int level, size_t n) {
         }
         {
             LaunchTimer lt(J, 1);
-            k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, h, lc, next, ctx->fb.p);
+            k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, sorted_order ? ht : h, h, sorted_order, lc, next, ctx->fb.p);
         }
         J.launches++;
         LAUNCHED("k_shade", J.st);

@@ -210,18 +210,6 @@ __global__ void k_hit_keys(HitQ h, const unsigned long long* __restrict__ lc, So
     keys[j] = g.bits < 30 ? m >> (30 - g.bits) : m;     // the top `bits` bits: coarser cells, fewer radix passes
     vals[j] = (int)j;
 }
-// dst[j] = src[order[j]]
-__global__ void k_permute_hits(HitQ src, HitQ dst, const unsigned long long* __restrict__ lc, const int* __restrict__ order) {
-    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (unsigned)lc[CTR_HITS]) return;
-    const unsigned s = (unsigned)order[j];
-#pragma unroll
-    for (int k = 0; k < 13; k++) dst.fld(k, j) = src.fld(k, s);
-    dst.pixel[j] = src.pixel[s];
-    dst.geom[j] = src.geom[s];
-    dst.meta[j] = src.meta[s];
-}
-
 // --intersection-only: pixel = 1/dist^2 on all channels (src/scene.cpp:69-70)
 __global__ void __launch_bounds__(RT_BLOCK) k_shade_io(HitQ h, const unsigned long long* ctr, double* fb,
                                                         unsigned long long* maxbits) {
@@ -249,7 +237,11 @@ __global__ void k_divide(double* fb, size_t n, const unsigned long long* maxbits
 }
 
 // Normal fix-up, ambient term, and the bounce spawn.
-__global__ void __launch_bounds__(RT_BLOCK) k_shade(DScene S, HitQ h, unsigned long long* ctr, RayQ next, double* fb) {
+// order != null (Morton-sorted level): hit j of this kernel is record order[j] of `src`
+// (k_trace's unsorted appends); the complete record goes to h[j], so the separate permutation
+// pass over the 116-byte records is folded into this kernel.  order == null: src is h itself.
+__global__ void __launch_bounds__(RT_BLOCK) k_shade(DScene S, HitQ src, HitQ h, const int* __restrict__ order,
+                                                     unsigned long long* ctr, RayQ next, double* fb) {
     unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = j < (unsigned)ctr[CTR_HITS];
     bool want_t = false, want_r = false;
@@ -258,18 +250,29 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(DScene S, HitQ h, unsigned l
     int pixel = 0, depth = 0, inside = 0;
     unsigned degenerate = 0;
     if (active) {
-        P = mk3(h.fld(0, j), h.fld(1, j), h.fld(2, j));
-        d3 N = mk3(h.fld(3, j), h.fld(4, j), h.fld(5, j));
-        d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
-        W[0] = h.fld(9, j); W[1] = h.fld(10, j); W[2] = h.fld(11, j);
-        pixel = h.pixel[j];
-        int meta = h.meta[j];
+        const unsigned s = order ? (unsigned)order[j] : j;
+        P = mk3(src.fld(0, s), src.fld(1, s), src.fld(2, s));
+        d3 N = mk3(src.fld(3, s), src.fld(4, s), src.fld(5, s));
+        d3 V = mk3(src.fld(6, s), src.fld(7, s), src.fld(8, s));
+        W[0] = src.fld(9, s); W[1] = src.fld(10, s); W[2] = src.fld(11, s);
+        pixel = src.pixel[s];
+        int meta = src.meta[s];
+        const int geom = src.geom[s];
         depth = meta & 0xff;
         inside = (meta >> 8) & 1;
-        const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
+        const DMat* m = S.mats + S.geoms[geom].mat;
         if (inside) N = -N;                                   // src/scene.cpp:72-73
         N = inplace_normalize(N);                             // src/scene.cpp:75
         h.fld(3, j) = N.x; h.fld(4, j) = N.y; h.fld(5, j) = N.z;
+        if (order) {
+            h.fld(0, j) = P.x; h.fld(1, j) = P.y; h.fld(2, j) = P.z;
+            h.fld(6, j) = V.x; h.fld(7, j) = V.y; h.fld(8, j) = V.z;
+            h.fld(9, j) = W[0]; h.fld(10, j) = W[1]; h.fld(11, j) = W[2];
+            h.fld(12, j) = src.fld(12, s);
+            h.pixel[j] = pixel;
+            h.geom[j] = geom;
+            h.meta[j] = meta;
+        }
         // ambient lights (src/scene.cpp:80-84)
         if (S.num_alights > 0) {
             double c[3] = {0, 0, 0};
