@@ -146,19 +146,57 @@ def reference_runs(pkg, wl_name, steps, warmup, target_s):
 # clocks sampler
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons during the timed region: NVML polled every 10 ms from a thread (the same
+    counters nvidia-smi prints; the timed region of a small workload is shorter than one nvidia-smi period),
+    falling back to `nvidia-smi -lms 100` when the NVML binding is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop_flag, self.nvml, self.source = threading.Event(), None, None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append([sm, mx] + ["Active" if r & b else "Not Active" for b in bits] + [0.0])
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.01)
+            self.nvml, self.source = pynvml, "nvml, 10 ms"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
+        self.source = "nvidia-smi -lms 100"
+
         def pump():
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -166,17 +204,21 @@ class ClockSampler:
         self.thread.start()
 
     def stop(self):
-        if not self.proc:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            if self.thread:
+                self.thread.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            if self.thread:
+                self.thread.join(timeout=2)
+        else:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        if self.thread:
-            self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 7:
                 continue
@@ -184,11 +226,11 @@ class ClockSampler:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if r[2 + k].lower().startswith("active"):
+            for k, nm in enumerate(self.NAMES):
+                if str(r[2 + k]).lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------
