@@ -709,7 +709,8 @@ int process_level(RenderJob& J, int level, size_t n) {
         }
         {
             LaunchTimer lt(J, 1);
-            k_shade<<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, sorted_order ? ht : h, h, sorted_order, lc, next, ctx->fb.p);
+            k_shade<<<(unsigned)((m + RT_SHADE_BLOCK - 1) / RT_SHADE_BLOCK), RT_SHADE_BLOCK, 0, J.st>>>(
+                ctx->S, sorted_order ? ht : h, h, sorted_order, lc, next, ctx->fb.p);
         }
         J.launches++;
         LAUNCHED("k_shade", J.st);
