@@ -19,7 +19,8 @@ lines = []
 for r in rows[a + 2:b]:
     if r[0] == "" or len(r) <= ith:
         continue
-    lines.append((int(r[ismp] or 0), int(r[iex] or 0), int(r[ith] or 0), int(r[ill] or 0), r[0], r[1]))
+    num = lambda v: int(v) if v.strip().lstrip("-").isdigit() else 0
+    lines.append((num(r[ismp]), num(r[iex]), num(r[ith]), num(r[ill]), r[0], r[1]))
 ts, te = sum(l[0] for l in lines), sum(l[1] for l in lines)
 print(f"total samples {ts}, warp instr {te}")
 for s, e, t, ll, no, src in sorted(lines, reverse=True)[:top]:
