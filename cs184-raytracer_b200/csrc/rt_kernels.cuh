@@ -364,7 +364,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
             // ... in tiles of RT_SHADOW_TILE hits: all lights of one tile are processed back to
             // back, so its hit records (116 B each) are fetched from DRAM once and re-read from
             // L2 by the other lights instead of streaming the whole queue once per light
-            const unsigned long long tile = t / ((unsigned long long)RT_SHADOW_TILE * nsl);
+            unsigned long long tile;
+            if (nhits * nsl <= 0xffffffffull) tile = (unsigned)t / (RT_SHADOW_TILE * nsl);     // 32-bit divide: ~5x cheaper
+            else tile = t / ((unsigned long long)RT_SHADOW_TILE * nsl);
             const unsigned long long first = tile * RT_SHADOW_TILE;
             const unsigned w = (unsigned)min((unsigned long long)RT_SHADOW_TILE, nhits - first);   // hits in this tile
             const unsigned r = (unsigned)(t - tile * RT_SHADOW_TILE * nsl);
