@@ -1,8 +1,10 @@
 // rt_api.cu — the C ABI of include/rt_b200.h: context, scene upload (flatten to device
 // SoA + LBVH build) and the render driver.  The driver is the GPU restatement of
 // Scene::renderScene (src/scene.cpp:10-59): instead of N threads pulling 2000-pixel
-// blocks and recursing per pixel, the frame is cut into batches of framebuffer slots and
-// every batch runs the wavefront loop  trace -> shade -> shadow  once per bounce level.
+// blocks and recursing per pixel, the frame is cut into batches of framebuffer slots (one
+// batch when the queues can hold it) and every batch runs the wavefront loop
+//   trace -> Morton sort of the hits -> shade -> shadow     once per bounce level,
+// with the shadow kernel of level l on its own stream beside trace/shade of level l+1.
 // Every level owns a ray queue of `cap` slots and a batch never exceeds cap/2 rays, so the
 // <= 2 children per hit (src/scene.cpp:127,134) can never overflow the next level.
 #include <algorithm>

@@ -1,7 +1,9 @@
 // rt_kernels.cuh — the wavefront kernels that replace the reference's recursion:
 //   k_raygen    src/scene.cpp:26-30 + Camera::calculateViewingRay src/rtbase.h:74-84
 //   k_trace     Scene::castRay src/scene.cpp:142-167 (closest hit) -> compacted hit queue
-//   k_shade     Scene::traceRay src/scene.cpp:72-85 (normal, ambient) and :114-136 (bounce spawn)
+//   k_hit_keys  (new) Morton key of every hit point; rt_sort.cuh sorts them (coherent warps downstream)
+//   k_shade     Scene::traceRay src/scene.cpp:72-85 (normal, ambient) and :114-136 (bounce spawn);
+//               gathers the hit records through the sorted index and writes the sorted queue
 //   k_shadow    Scene::traceRay src/scene.cpp:86-107 (one thread per hit x shadow light)
 //   k_resolve   src/scene.cpp:31 (pixel store) + optional src/writers.cpp:7 quantisation
 // The recursion becomes an iterative bounce loop: a queued ray carries its pixel, the RGB
