@@ -3,4 +3,3 @@ for n in 8 4 2; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
 done
 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
-python -m pytest tests/test_gpu_parity.py -q -m gpu -k "intersection_only_across or tile_sharding" 2>&1 | tail -2
