@@ -2,11 +2,15 @@
 """bench.py — Mrays/s of the per-pixel trace loop (BASELINE.json metric) on 1..8 B200.
 
 A "step" is one frame of the workload rendered by the hot path: ray generation, wavefront
-trace/shade/shadow loop over all bounce levels, device-side 8-bit resolve and (N > 1) the
-NCCL gather of the interleaved tiles to rank 0.  A "ray" is one reference castRay call
-(primary + shadow + secondary; reference src/scene.cpp:65,91,127,134).
+trace/shade/shadow loop over all bounce levels and the device-side 8-bit resolve.  With N > 1
+ranks every rank's resolve kernel stores its interleaved tiles straight into ONE frame in rank
+0's memory (CUDA IPC mapping, NVLink peer stores: rt_shared_frame_* + RT_FLAG_FULL_FRAME), so
+there is no gather collective and no unpack pass; `--assemble nccl` keeps round 1's
+dist.gather + unpack as the A/B.  A "ray" is one reference castRay call (primary + shadow +
+secondary; reference src/scene.cpp:65,91,127,134).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+                  [--assemble peer|nccl] [--configs all|none]
 
 N > 1 is launched by the driver with torch.distributed.run (one rank per GPU, NCCL).
 `--impl reference` times the reference's own CPU implementation of the path
@@ -17,6 +21,7 @@ Only the cpu_baseline leg and `--impl reference` execute anything under oracle/.
 """
 import argparse
 import ctypes as C
+import hashlib
 import importlib.util
 import json
 import os
@@ -234,6 +239,416 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------
+class RawDevice:
+    """__cuda_array_interface__ over a raw device pointer, so torch can view library-owned memory."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+# stored outputs of the UNMODIFIED reference (tests/golden/make_fixtures.py) each workload is checked against, and
+# the frame size of that check (the fixture's size: full size where the reference finishes in a minute of CPU)
+PARITY_FIXTURE = {
+    "synthetic": ("synthetic_96x54.npz", 96, 54), "synthetic4k": ("synthetic_96x54.npz", 96, 54),
+    "teapot": ("big_input-02_1920x1080.npz", 1920, 1080), "refraction3": ("big_refraction3_3840x2160.npz", 3840, 2160),
+    "bunny": ("big_bunny4_960x540.npz", 960, 540), "input01": ("input-01_96x96.npz", 96, 96),
+}
+
+
+def parity_check(pkg, ren, wl_name):
+    """Single-GPU render of the workload's scene at its fixture size against the reference's stored output:
+    primary hit ids (geometry and face) and the castRay count exact, frame within 1e-9 (FP64) or equal (8-bit)."""
+    fname, w, h = PARITY_FIXTURE[wl_name]
+    path = GOLDEN / "ref" / fname
+    if not path.exists():
+        return {"against": fname, "ok": None, "note": "fixture missing"}
+    fx = np.load(path)
+    depth = int(fx["depth"])
+    rgb = ren.render(w, h, depth)
+    st = ren.stats()
+    geom, face = ren.primary_ids(w, h)
+    ids_ok = bool(np.array_equal(geom, fx["geom"].astype(np.int32)) and np.array_equal(face, fx["face"]))
+    count_ok = st["rays_primary"] + st["rays_shadow"] + st["rays_secondary"] == int(fx["castray_calls"])
+    if "rgb" in fx:
+        err = float(np.abs(rgb - fx["rgb"]).max())
+    else:
+        s = int(fx["stride"])
+        err = float(np.abs(rgb[::s, ::s] - fx["rgb_sub"]).max())
+    return {"against": f"tests/golden/ref/{fname} (unmodified reference, {w}x{h}, depth {depth})", "ids_equal": ids_ok,
+            "ray_count_equal": bool(count_ok), "max_abs_diff_fp64": err, "ok": bool(ids_ok and count_ok and err <= 1e-9)}
+
+
+def load_traffic(wl_name):
+    tf = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(tf.read_text()).get(wl_name, {})
+    except Exception:
+        return {}
+
+
+def run_workload(args, pkg, torch, dist, wl_name, headline):
+    """Times one workload at the launched world size.  Returns the fields of its JSON record (rank 0) or None."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    spec, width, height, depth, desc = WORKLOADS[wl_name]
+    steps, warmup = (args.steps, args.warmup) if headline else (min(args.steps, 5), max(min(args.warmup, 3), 3))
+    nbytes = height * width * 3
+    config = {"workload": f"{wl_name}: {desc}", "width": width, "height": height, "bounce_depth": depth,
+              "partition": f"interleaved 32x32 tiles over {world} rank(s), scene replicated",
+              "assemble": "single rank: row-major RGB8 frame on the device" if world == 1 else
+                          ("peer: every rank's resolve kernel stores its tiles into rank 0's frame (CUDA IPC mapping, NVLink), "
+                           "one 4-byte all-reduce per frame as the completion barrier" if args.assemble == "peer" else
+                           "nccl: dist.gather of the packed RGB8 tiles + unpack kernel on rank 0 (round-1 path, A/B)"),
+              "l2": "no explicit flush: every frame streams its ray and hit queues (80 B / 116 B per record, 10^6..10^8 records per bounce "
+                    "level) through the 126 MB L2 between two uses of any scene data"}
+
+    host_scene = build_scene(pkg, spec)
+    ren = pkg.Renderer(local_rank)
+    ren.upload(host_scene)
+    up_stats = ren.stats()
+    stream = torch.cuda.current_stream().cuda_stream
+    base_flags = pkg.RT_FLAG_TIME_KERNELS
+    peer = world > 1 and args.assemble == "peer"
+    shared_flag = pkg.RT_FLAG_FULL_FRAME if peer else 0
+    p = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world, flags=base_flags | shared_flag)
+    emulate = os.environ.get("RT_BENCH_EMULATE_RANK")      # "r/n": time rank r's share of an n-rank job on one GPU (development aid)
+    if emulate and world == 1:
+        er, en = (int(x) for x in emulate.split("/"))
+        p = pkg.make_params(width, height, depth, tile_rank=er, tile_world=en, flags=base_flags)
+        config["partition"] = f"EMULATED rank {er} of {en} (its tiles only, no gather)"
+    own_tiles, max_tiles, total_tiles = pkg.tile_counts(p)
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
+    shared_ptr = None
+    frame = gathered = packed_all = None
+    if world == 1 and emulate:
+        out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
+        out_ptr = out.data_ptr()
+    elif world == 1:
+        frame = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out_ptr = frame.data_ptr()
+    elif peer:
+        handle = [None]
+        if rank == 0:
+            shared_ptr, h = ren.shared_frame_create(nbytes)
+            handle = [h]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            shared_ptr = ren.shared_frame_open(handle[0])
+        out_ptr = shared_ptr
+        if rank == 0:
+            frame = torch.as_tensor(RawDevice(shared_ptr, nbytes), device=dev)
+            frame.zero_()
+    else:
+        out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
+        out_ptr = out.data_ptr()
+        # rank r's tiles land in slice r of one buffer: the gather writes them in place (no concatenation pass)
+        packed_all = torch.empty(world * out.numel(), dtype=torch.uint8, device=dev) if rank == 0 else None
+        gathered = list(packed_all.chunk(world)) if rank == 0 else None
+        frame = torch.empty(nbytes, dtype=torch.uint8, device=dev) if rank == 0 else None
+
+    def assemble(pp):
+        """What follows a rank's render until the frame is complete on rank 0."""
+        if world == 1:
+            return
+        if peer:
+            dist.all_reduce(tick)               # completion barrier: all ranks' peer stores have been synchronised
+        else:
+            dist.gather(out, gathered, dst=0)
+            if rank == 0:
+                ren.unpack_tiles(pp, packed_all.data_ptr(), frame.data_ptr(), rgb8=True, stream=stream)
+
+    def step():
+        ren.render_device(p, out_ptr, rgb8=True, stream=stream)
+        assemble(p)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 0)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"ms_kernel": np.zeros(4), "launches_kernel": np.zeros(4), "launches": 0}
+    e0.record()
+    for _ in range(steps):
+        step()
+        st = ren.stats()
+        agg["ms_kernel"] += np.array(st["ms_kernel"]); agg["launches_kernel"] += np.array(st["launches_kernel"])
+        agg["launches"] += st["kernel_launches"] + (1 if (world > 1 and rank == 0 and not peer) else 0)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    rays = torch.tensor([st["rays_primary"], st["rays_shadow"], st["rays_secondary"], agg["launches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    ms_total = float(ms_total.item())
+    rays_cls = [int(x) for x in rays[:3].tolist()]
+    rays_frame = sum(rays_cls)
+    launches_total = int(rays[3].item())
+    value = rays_frame * steps / (ms_total * 1e-3) / 1e6
+
+    # ---------------- the assembled frame against a single-rank render of the same frame (rank 0, after the timed region)
+    frame_check = None
+    if world > 1 and rank == 0:
+        multi = frame.clone()
+        single = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ren.render_device(pkg.make_params(width, height, depth), single.data_ptr(), rgb8=True, stream=stream)
+        torch.cuda.synchronize()
+        diff = (multi.to(torch.int16) - single.to(torch.int16)).abs()
+        frame_check = {"frame_matches_single_rank": bool(torch.equal(multi, single)), "max_abs_diff_8bit": int(diff.max().item()),
+                       "values_differing": int((diff != 0).sum().item()),
+                       "sha256_multi": hashlib.sha256(multi.cpu().numpy().tobytes()).hexdigest()[:16],
+                       "sha256_single": hashlib.sha256(single.cpu().numpy().tobytes()).hexdigest()[:16]}
+        del multi, single, diff
+    if world > 1:
+        dist.barrier()
+
+    # ---------------- end-to-end: HOST buffers in, HOST frame out, every step
+    #   N = 1: rt_scene_upload from (pinned) host arrays + LBVH build + rt_render_rgb8 into a pinned host frame.
+    #   N > 1: every rank copies 1/N of the face arrays over its own PCIe link, one NCCL all-gather over NVLink
+    #          replicates them, rt_scene_upload takes them on the device (RT_SCENE_FACES_ON_DEVICE) and builds the LBVH;
+    #          the host frame lives in shared memory every rank has page-locked, and each rank's resolve kernel
+    #          stores its own tiles into it over its own PCIe link (no funnel through rank 0).
+    e2e = None
+    if not args.no_e2e and not emulate:
+        flat = host_scene.flat.contents
+        cudart = torch.cuda.cudart()
+        nf = int(flat.num_faces)
+        pinned = []
+
+        def pin(addr, n):
+            if n and addr and cudart.cudaHostRegister(addr, n, 0) in (0, cudart.cudaError.success):
+                pinned.append(addr)
+                return True
+            return False
+        pts_addr = C.cast(flat.face_points, C.c_void_p).value
+        nrm_addr = C.cast(flat.face_normals, C.c_void_p).value
+        pin(pts_addr, nf * 72)
+        pin(nrm_addr, nf * 72)
+        shm_path = None
+        host_shared = False
+        if world == 1:
+            host_frame = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            host_np = host_frame.numpy()
+            host_shared = True
+        else:
+            name = [f"/dev/shm/rt_b200_frame_{os.getpid()}_{wl_name}" if rank == 0 else None]
+            dist.broadcast_object_list(name, src=0)
+            shm_path = name[0]
+            if rank == 0:
+                np.zeros(nbytes, np.uint8).tofile(shm_path)
+            dist.barrier()
+            host_np = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+            ok = torch.tensor([1 if pin(host_np.ctypes.data, nbytes) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            host_shared = bool(ok.item())
+        pe = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world,
+                             flags=pkg.RT_FLAG_FULL_FRAME if world > 1 else 0)
+        split_upload = world > 1 and nf >= 4096
+        if split_upload:
+            per = (nf + world - 1) // world
+            pts_np = np.ctypeslib.as_array(flat.face_points, shape=(nf * 9,))
+            nrm_np = np.ctypeslib.as_array(flat.face_normals, shape=(nf * 9,))
+            lo, hi = min(rank * per, nf), min((rank + 1) * per, nf)
+            h_slice = torch.zeros(2, per * 9, dtype=torch.float64).pin_memory()
+            h_slice[0, :(hi - lo) * 9] = torch.from_numpy(pts_np[lo * 9:hi * 9])
+            h_slice[1, :(hi - lo) * 9] = torch.from_numpy(nrm_np[lo * 9:hi * 9])
+            d_slice = torch.empty(2, per * 9, dtype=torch.float64, device=dev)
+            d_all = torch.empty(world, 2, per * 9, dtype=torch.float64, device=dev)
+            d_pts = torch.empty(world * per * 9, dtype=torch.float64, device=dev)
+            d_nrm = torch.empty(world * per * 9, dtype=torch.float64, device=dev)
+            dev_scene = pkg.rt_scene()
+            C.memmove(C.byref(dev_scene), C.byref(flat), C.sizeof(pkg.rt_scene))
+            dev_scene.flags = pkg.RT_SCENE_FACES_ON_DEVICE
+            dev_scene.face_points = C.cast(C.c_void_p(d_pts.data_ptr()), C.POINTER(C.c_double))
+            dev_scene.face_normals = C.cast(C.c_void_p(d_nrm.data_ptr()), C.POINTER(C.c_double))
+
+        def e2e_step():
+            if split_upload:
+                d_slice.copy_(h_slice, non_blocking=True)                    # 1/N of the faces over this rank's PCIe link
+                dist.all_gather_into_tensor(d_all, d_slice)                   # NVLink
+                d_pts.view(world, per * 9).copy_(d_all[:, 0])                # rank-major slices -> the two face arrays
+                d_nrm.view(world, per * 9).copy_(d_all[:, 1])
+                torch.cuda.synchronize()
+                ren.upload(C.pointer(dev_scene))
+            else:
+                ren.upload(host_scene)
+            if host_shared:
+                ren.render_host_params(pe, host_np.ctypes.data, rgb8=True)   # tiles stored straight into the host frame
+                if world > 1:
+                    dist.all_reduce(tick)
+            else:                                                            # fallback: peer frame on rank 0, one D2H
+                ren.render_device(p, out_ptr, rgb8=True, stream=stream)
+                assemble(p)
+                if rank == 0:
+                    torch.from_numpy(host_np).copy_(frame)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        sync_all()
+        n_e2e = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        sync_all()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        st_e = ren.stats()
+        h2d = int(st_e["scene_bytes_h2d"]) + (int(h_slice.numel()) * 8 if split_upload else 0)
+        h2d_t = torch.tensor([h2d], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
+        e2e_matches = None
+        if rank == 0 and frame is not None and not emulate:
+            ref8 = frame.cpu().numpy()
+            d = np.abs(np.asarray(host_np).astype(np.int16) - ref8.astype(np.int16))
+            e2e_matches = {"equal_to_device_frame": bool(d.max() == 0), "max_abs_diff_8bit": int(d.max())}
+        e2e = {"value": rays_frame * n_e2e / float(t_e2e.item()) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": int(h2d_t.item()), "d2h_bytes_per_step": nbytes,
+               "ms_per_step": 1e3 * float(t_e2e.item()) / n_e2e,
+               "ms_scene_upload": st_e["ms_upload"], "ms_lbvh_build": st_e["ms_build"], "steps": n_e2e,
+               "host_frame": e2e_matches,
+               "path": ("rt_scene_upload (pinned host arrays) + LBVH build + rt_render_rgb8 into a pinned host frame" if world == 1 else
+                        ("per-rank 1/N face slices H2D + NCCL all-gather + rt_scene_upload(RT_SCENE_FACES_ON_DEVICE) + LBVH build on every rank" if split_upload
+                         else "rt_scene_upload on every rank") +
+                        (" + rt_render_rgb8(RT_FLAG_FULL_FRAME): every rank stores its tiles into one page-locked shared-memory host frame over its own PCIe link"
+                         if host_shared else " + peer-store frame on rank 0 + one D2H"))}
+        for addr in pinned:
+            cudart.cudaHostUnregister(addr)
+        if shm_path:
+            del host_np
+            if world > 1:
+                dist.barrier()
+            if rank == 0:
+                try:
+                    os.unlink(shm_path)
+                except OSError:
+                    pass
+        if split_upload:
+            ren.upload(host_scene)
+
+    # ---------------- roofline of the traversal kernels (rank 0; its own share of the frame when N > 1)
+    roofline = None
+    if rank == 0:
+        ptile = dict(tile_rank=p.tile_rank, tile_world=p.tile_world)
+        scratch = torch.empty(max(max_tiles * pkg.RT_TILE_PIXELS * 3, nbytes if world == 1 and not emulate else 0), dtype=torch.uint8, device=dev)
+        # one frame with the kernels strictly serialised: durations per kernel class that add up to the frame
+        # (in the timed region k_shadow of level l runs beside k_trace / k_shade of level l+1)
+        ps = pkg.make_params(width, height, depth, flags=pkg.RT_FLAG_TIME_KERNELS | pkg.RT_FLAG_SERIAL, **ptile)
+        ren.render_device(ps, scratch.data_ptr(), rgb8=True, stream=stream)
+        serial = ren.stats()
+        pc = pkg.make_params(width, height, depth, flags=pkg.RT_FLAG_COUNT_WORK, **ptile)
+        ren.render_device(pc, scratch.data_ptr(), rgb8=True, stream=stream)
+        cs = ren.stats()
+        names = ["k_trace", "k_shade", "k_shadow", "other"]
+        ser = np.array(serial["ms_kernel"])
+        dom = int(np.argmax(ser[:3]))
+        node_bytes, face_bytes = ren.device_bytes()
+        peak_hbm, peak_src = 6650.0, "fallback"
+        try:
+            mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+            peak_hbm, peak_src = float(mp["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        traffic_all = load_traffic(wl_name)
+        lanes_all = traffic_all.get("active_lanes", {})
+        if node_bytes > 0:
+            walk_c, _ = ren.microbench_node_walk(32, 64)
+            walk_d, _ = ren.microbench_node_walk(1, 64)
+        else:
+            walk_c = walk_d = None
+        per_kernel = {}
+        for kname, k, cls in (("k_trace", 0, 0), ("k_shadow", 1, 2)):
+            ms_k = float(ser[cls])
+            visits = cs["nodes_fetched"][k] / 4.0              # wide-node visits (4 child boxes each)
+            nrays = (cs["rays_primary"] + cs["rays_secondary"]) if k == 0 else cs["rays_shadow"]
+            ach = visits / (ms_k * 1e-3) if ms_k > 0 else 0.0
+            tr = traffic_all.get(kname)
+            per_kernel[kname] = {
+                "ms_serial_frame": ms_k, "rays": int(nrays), "node_visits": visits, "visits_per_ray": visits / max(nrays, 1),
+                "exact_tests_per_ray": (cs["tris_tested"][k] + cs["spheres_tested"][k]) / max(nrays, 1),
+                "achieved_gvisits_s": ach / 1e9,
+                "frac_of_coherent_walk": ach / walk_c if walk_c else None,
+                "frac_of_divergent_walk": ach / walk_d if walk_d else None,
+                "lsu_bytes_gbs": ach * 112 / 1e9,
+                "active_lanes_per_instruction_ncu": lanes_all.get(kname),
+                "dram_bytes_per_frame_ncu": tr,
+                "dram_gbs": (tr / (ms_k * 1e-3) / 1e9) if (tr and ms_k > 0) else None,
+                "dram_frac_of_hbm_peak": (tr / (ms_k * 1e-3) / 1e9 / peak_hbm) if (tr and ms_k > 0) else None}
+        domk = names[dom] if names[dom] in per_kernel else "k_shadow"
+        dk = per_kernel[domk]
+        n_launch = max(serial["launches_kernel"][0 if domk == "k_trace" else 2], 1)
+        roofline = {
+            # The traversal kernels are bound by the rate at which L1TEX/L2 feed 112-byte node visits to partly divergent
+            # warps, not by DRAM (ncu: DRAM 2 % of peak, L1TEX 80-85 %, LSU data pipe 66-82 % busy).  The ceiling is measured
+            # on the real node array by rt_microbench_node_walk (the traversal's loads and nothing else, fully coherent warps).
+            "bound": "l1tex-node-gather (not hbm: see dram_frac_of_hbm_peak)", "kernel": domk,
+            "achieved": dk["achieved_gvisits_s"], "peak": (walk_c / 1e9) if walk_c else None, "unit": "G wide-node visits/s",
+            "frac": dk["frac_of_coherent_walk"], "peak_source": "measured in this run: rt_microbench_node_walk(group=32) on the scene's LBVH",
+            "traffic": (dk["dram_bytes_per_frame_ncu"] / n_launch) if dk["dram_bytes_per_frame_ncu"] else None,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full, profiles/traffic.json)",
+            "launches_per_step": n_launch, "ms_per_launch": dk["ms_serial_frame"] / n_launch,
+            "hbm_peak_gbs": peak_hbm, "hbm_peak_source": peak_src,
+            "node_walk_gvisits_s": {"coherent_warp": (walk_c / 1e9) if walk_c else None, "divergent_lanes": (walk_d / 1e9) if walk_d else None},
+            "kernels": per_kernel,
+            "kernel_share_of_step": float(ser[0 if domk == "k_trace" else 2] / max(serial["ms_trace"], 1e-9)),
+            "ms_kernel_per_step": {n: float(v / steps) for n, v in zip(names, agg["ms_kernel"])},
+            "ms_kernel_serial_frame": {n: float(v) for n, v in zip(names, serial["ms_kernel"])},
+            "ms_serial_frame": float(serial["ms_trace"]),
+            "duration_source": "RT_FLAG_SERIAL frame after the timed region (CUDA events around every launch on the launching stream)",
+            "note": "ms_kernel_per_step: event-bracketed durations inside the timed region, where k_trace/k_shade of "
+                    "bounce level l+1 run beside k_shadow of level l (brackets overlap); ms_kernel_serial_frame: one extra "
+                    "frame with RT_FLAG_SERIAL, classes add up to ms_serial_frame",
+            "node_array_bytes": node_bytes, "face_record_bytes": face_bytes,
+            "work_per_step": {"box_tests": cs["nodes_fetched"], "tris": cs["tris_tested"], "spheres": cs["spheres_tested"],
+                              "hits": cs["hits"], "shadow_lights": int(cs["rays_shadow"] // max(cs["hits"], 1))}}
+        del scratch
+
+    # ---------------- parity of this workload against the stored reference output (rank 0, single-GPU render)
+    parity = parity_check(pkg, ren, wl_name) if rank == 0 else None
+
+    # ---------------- cpu baseline (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not emulate:
+        try:
+            r = reference_runs(pkg, wl_name, 1, 0, target_s=12.0 if headline else 3.0)
+            cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+        except FileNotFoundError as e:
+            cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    if peer and shared_ptr is not None:
+        frame = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank != 0:
+            ren.shared_frame_close(shared_ptr)
+        dist.barrier()
+        if rank == 0:
+            ren.shared_frame_close(shared_ptr)
+    ren.close()
+    host_scene.close()
+    if rank != 0:
+        return None
+    return {"value": value, "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup, "config": config,
+            "rays_per_step": {"primary": rays_cls[0], "shadow": rays_cls[1], "secondary": rays_cls[2]},
+            "frame_ms": ms_total / steps, "ms_scene_upload": up_stats["ms_upload"], "ms_lbvh_build": up_stats["ms_build"],
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity, "frame_check": frame_check}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,6 +656,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="synthetic", choices=sorted(WORKLOADS))
+    ap.add_argument("--assemble", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = resolve kernels store into rank 0's frame over NVLink (default); nccl = gather + unpack (A/B)")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="all: after the headline workload also time the other BASELINE.json configs (per_config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -250,17 +669,14 @@ def main():
     if world == 1 and args.gpus != 1:
         print(f"bench.py: --gpus {args.gpus} needs torch.distributed.run (WORLD_SIZE={world})", file=sys.stderr)
         sys.exit(2)
-    spec, width, height, depth, desc = WORKLOADS[args.workload]
     pkg = load_package()
-    config = {"workload": f"{args.workload}: {desc}", "width": width, "height": height, "bounce_depth": depth,
-              "partition": f"interleaved 32x32 tiles over {world} rank(s), scene replicated",
-              "l2": "no explicit flush: every frame streams its ray and hit queues (80 B / 116 B per record, 10^6..10^8 records per bounce "
-                    "level) through the 126 MB L2 between two uses of any scene data"}
 
     # -------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return
+        spec, width, height, depth, desc = WORKLOADS[args.workload]
+        config = {"workload": f"{args.workload}: {desc}", "width": width, "height": height, "bounce_depth": depth}
         try:
             r = reference_runs(pkg, args.workload, args.steps, max(args.warmup, 0), target_s=6.0)
         except FileNotFoundError as e:
@@ -282,208 +698,35 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    host_scene = build_scene(pkg, spec)
-    ren = pkg.Renderer(local_rank)
-    ren.upload(host_scene)
-    up_stats = ren.stats()
-    stream = torch.cuda.current_stream().cuda_stream
-    base_flags = pkg.RT_FLAG_TIME_KERNELS
-    p = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world, flags=base_flags)
-    emulate = os.environ.get("RT_BENCH_EMULATE_RANK")      # "r/n": time rank r's share of an n-rank job on one GPU (development aid)
-    if emulate and world == 1:
-        er, en = (int(x) for x in emulate.split("/"))
-        p = pkg.make_params(width, height, depth, tile_rank=er, tile_world=en, flags=base_flags)
-        config["partition"] = f"EMULATED rank {er} of {en} (its tiles only, no gather)"
-    own_tiles, max_tiles, total_tiles = pkg.tile_counts(p)
-    if world == 1 and emulate:
-        out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
-        gathered = frame = None
-        args.no_e2e = True
-    elif world == 1:
-        out = torch.empty(height * width * 3, dtype=torch.uint8, device=dev)
-        gathered = frame = None
-    else:
-        out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
-        # rank r's tiles land in slice r of one buffer: the gather writes them in place (no concatenation pass)
-        packed_all = torch.empty(world * out.numel(), dtype=torch.uint8, device=dev) if rank == 0 else None
-        gathered = list(packed_all.chunk(world)) if rank == 0 else None
-        frame = torch.empty(height * width * 3, dtype=torch.uint8, device=dev) if rank == 0 else None
-
-    def step():
-        ren.render_device(p, out.data_ptr(), rgb8=True, stream=stream)
-        if world > 1:
-            dist.gather(out, gathered, dst=0)
+    head = run_workload(args, pkg, torch, dist, args.workload, True)
+    per_config = {}
+    emulate = os.environ.get("RT_BENCH_EMULATE_RANK")
+    if args.configs == "all" and args.workload == "synthetic" and not emulate:
+        # the other BASELINE.json configurations at this N (configs[0..3]); the headline above is configs[4]
+        for name in ("input01", "teapot", "refraction3", "bunny"):
+            rec = run_workload(args, pkg, torch, dist, name, False)
             if rank == 0:
-                ren.unpack_tiles(p, packed_all.data_ptr(), frame.data_ptr(), rgb8=True, stream=stream)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 0)):
-        step()
-    sync_all()
-    sampler = ClockSampler(local_rank)
+                rf = rec["roofline"] or {}
+                per_config[name] = {
+                    "workload": rec["config"]["workload"], "value": rec["value"], "unit": "Mrays/s", "ms_per_step": rec["ms_per_step"],
+                    "steps": rec["steps"], "rays_per_step": rec["rays_per_step"], "gpu_launches": rec["gpu_launches"],
+                    "e2e": {k: rec["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")} if rec["e2e"] else None,
+                    "parity": rec["parity"], "frame_check": rec["frame_check"],
+                    "roofline": {"kernel": rf.get("kernel"), "frac": rf.get("frac"), "achieved": rf.get("achieved"), "peak": rf.get("peak"),
+                                 "unit": rf.get("unit"), "ms_kernel_serial_frame": rf.get("ms_kernel_serial_frame")},
+                    "cpu_baseline": rec["cpu_baseline"]}
     if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"ms_kernel": np.zeros(4), "launches_kernel": np.zeros(4), "launches": 0}
-    e0.record()
-    for _ in range(args.steps):
-        step()
-        st = ren.stats()
-        agg["ms_kernel"] += np.array(st["ms_kernel"]); agg["launches_kernel"] += np.array(st["launches_kernel"])
-        agg["launches"] += st["kernel_launches"] + (1 if (world > 1 and rank == 0) else 0)
-    e1.record()
-    sync_all()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    rays = torch.tensor([st["rays_primary"], st["rays_shadow"], st["rays_secondary"], agg["launches"]], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
-    ms_total = float(ms_total.item())
-    rays_cls = [int(x) for x in rays[:3].tolist()]
-    rays_frame = sum(rays_cls)
-    launches_total = int(rays[3].item())
-    value = rays_frame * args.steps / (ms_total * 1e-3) / 1e6
-
-    # ---------------- end-to-end: scene upload (H2D) + LBVH build + render + gather + D2H, host buffers
-    e2e = None
-    if not args.no_e2e:
-        flat = host_scene.flat.contents
-        cudart = torch.cuda.cudart()
-        nf = flat.num_faces
-        pinned = []
-        for ptr in (flat.face_points, flat.face_normals):
-            addr = C.cast(ptr, C.c_void_p).value
-            if nf and addr and cudart.cudaHostRegister(addr, nf * 72, 0) in (0, cudart.cudaError.success):
-                pinned.append(addr)
-        host_frame = torch.empty(height * width * 3, dtype=torch.uint8, pin_memory=True)
-        pe = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world)
-
-        def e2e_step():
-            ren.upload(host_scene)
-            ren.render_device(pe, out.data_ptr(), rgb8=True, stream=stream)
-            if world > 1:
-                dist.gather(out, gathered, dst=0)
-                if rank == 0:
-                    ren.unpack_tiles(pe, packed_all.data_ptr(), frame.data_ptr(), rgb8=True, stream=stream)
-                    host_frame.copy_(frame, non_blocking=True)
-            else:
-                host_frame.copy_(out, non_blocking=True)
-            torch.cuda.synchronize()
-
-        e2e_step()
-        sync_all()
-        n_e2e = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        sync_all()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        st_e = ren.stats()
-        e2e = {"value": rays_frame * n_e2e / float(t_e2e.item()) / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": int(st_e["scene_bytes_h2d"]) * world, "d2h_bytes_per_step": height * width * 3,
-               "ms_per_step": 1e3 * float(t_e2e.item()) / n_e2e,
-               "ms_scene_upload": st_e["ms_upload"], "ms_lbvh_build": st_e["ms_build"], "steps": n_e2e,
-               "path": "rt_scene_upload (host arrays, pinned) + rt_render_device_rgb8 + NCCL gather + D2H into pinned host frame"}
-        for addr in pinned:
-            cudart.cudaHostUnregister(addr)
-
-    # ---------------- roofline of the dominant kernel (rank 0)
-    roofline = None
-    if rank == 0:
-        # one frame with the kernels strictly serialised: durations per kernel class that add up to the frame
-        # (in the timed region k_shadow of level l runs beside k_trace / k_shade of level l+1)
-        ps = pkg.make_params(width, height, depth, tile_rank=p.tile_rank, tile_world=p.tile_world,
-                             flags=pkg.RT_FLAG_TIME_KERNELS | pkg.RT_FLAG_SERIAL)
-        ren.render_device(ps, out.data_ptr(), rgb8=True, stream=stream)
-        serial = ren.stats()
-        pc = pkg.make_params(width, height, depth, tile_rank=p.tile_rank, tile_world=p.tile_world, flags=pkg.RT_FLAG_COUNT_WORK)
-        ren.render_device(pc, out.data_ptr(), rgb8=True, stream=stream)
-        cs = ren.stats()
-        names = ["k_trace", "k_shade", "k_shadow", "other"]
-        # dominance from the serialised frame (the overlapped k_trace bracket also counts its wait for SMs)
-        dom = int(np.argmax(np.array(serial["ms_kernel"])[:3]))
-        nsl = cs["rays_shadow"] // max(cs["hits"], 1)
-        # algorithmic bytes: 32 B per BVH child box tested, 80 B per exact
-        # face test, 128 B per sphere test, + the kernel's queue records
-        if dom == 2:
-            k = 1
-            queue = cs["hits"] * 116 + cs["rays_shadow"] * 24
-        elif dom == 0:
-            k = 0
-            queue = (cs["rays_primary"] + cs["rays_secondary"]) * 80 + cs["hits"] * 116
-        else:
-            k = None
-            queue = cs["hits"] * (116 + 24) + cs["rays_secondary"] * 80
-        bytes_frame = queue
-        if k is not None:
-            bytes_frame += 32 * cs["nodes_fetched"][k] + 80 * cs["tris_tested"][k] + 128 * cs["spheres_tested"][k]
-        n_launch = max(agg["launches_kernel"][dom] / args.steps, 1)
-        if dom == 0:
-            # k_trace shares the GPU with the previous level's k_shadow in the timed region: take its
-            # duration from the serialised frame instead
-            ms_launch = serial["ms_kernel"][0] / max(serial["launches_kernel"][0], 1)
-            dur_src = "RT_FLAG_SERIAL frame after the timed region (CUDA events on the launching stream)"
-        else:
-            ms_launch = agg["ms_kernel"][dom] / max(agg["launches_kernel"][dom], 1)
-            dur_src = "timed region (CUDA events on the stream the kernel is launched on)"
-        achieved = bytes_frame / n_launch / (ms_launch * 1e-3) / 1e9
-        peak, peak_src = 6650.0, "fallback"
-        try:
-            mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-            peak, peak_src = float(mp["hbm_gbs"]), "measured"
-        except Exception:
-            pass
-        node_bytes, face_bytes = ren.device_bytes()
-        gather = ren.microbench_gather(max(node_bytes, 1 << 20), 64)
-        traffic = None
-        tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists():
-            try:
-                traffic = json.loads(tf.read_text()).get(args.workload, {}).get(names[dom])
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "bytes_per_launch": bytes_frame / n_launch, "ms_per_launch": ms_launch, "launches_per_step": n_launch,
-                    "duration_source": dur_src,
-                    "kernel_share_of_step": float(serial["ms_kernel"][dom] / max(serial["ms_trace"], 1e-9)),
-                    "ms_kernel_per_step": {n: float(v / args.steps) for n, v in zip(names, agg["ms_kernel"])},
-                    "ms_kernel_serial_frame": {n: float(v) for n, v in zip(names, serial["ms_kernel"])},
-                    "ms_serial_frame": float(serial["ms_trace"]),
-                    "note": "ms_kernel_per_step: event-bracketed durations inside the timed region, where k_trace/k_shade of "
-                            "bounce level l+1 run beside k_shadow of level l (k_trace's bracket includes waiting for SMs); "
-                            "ms_kernel_serial_frame: one extra frame with RT_FLAG_SERIAL, classes add up to ms_serial_frame",
-                    "node_gather_gbs": gather, "frac_of_node_gather": achieved / gather if gather else None,
-                    "node_array_bytes": node_bytes, "face_record_bytes": face_bytes,
-                    "work_per_step": {"nodes": cs["nodes_fetched"], "tris": cs["tris_tested"], "spheres": cs["spheres_tested"],
-                                      "hits": cs["hits"], "shadow_lights": int(nsl)}}
-
-    # ---------------- cpu baseline (rank 0, N = 1)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            r = reference_runs(pkg, args.workload, 1, 0, target_s=12.0)
-            cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
-        except FileNotFoundError as e:
-            cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
-
-    if rank == 0:
-        line = {"metric": "Mrays/s (primary+shadow+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "rays_per_step": {"primary": rays_cls[0], "shadow": rays_cls[1], "secondary": rays_cls[2]},
-                "frame_ms": ms_total / args.steps, "ms_scene_upload": up_stats["ms_upload"], "ms_lbvh_build": up_stats["ms_build"],
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu}
+        line = {"metric": "Mrays/s (primary+shadow+secondary)", "value": head["value"], "unit": "Mrays/s", "n_gpus": world,
+                "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": head["config"],
+                "rays_per_step": head["rays_per_step"], "frame_ms": head["frame_ms"], "ms_scene_upload": head["ms_scene_upload"],
+                "ms_lbvh_build": head["ms_lbvh_build"], "clocks": head["clocks"], "e2e": head["e2e"],
+                "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"],
+                "parity": head["parity"]}
+        if head["frame_check"]:
+            line.update(head["frame_check"])
+        if per_config:
+            line["per_config"] = per_config
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

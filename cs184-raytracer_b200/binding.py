@@ -27,6 +27,9 @@ RT_FLAG_BRUTE_FORCE = 1
 RT_FLAG_COUNT_WORK = 2
 RT_FLAG_TIME_KERNELS = 4
 RT_FLAG_SERIAL = 8
+RT_FLAG_FULL_FRAME = 16
+RT_SCENE_FACES_ON_DEVICE = 1
+RT_ERR_LIMIT = -6
 RT_TILE_PIXELS = int(os.environ.get("RT_B200_TILE", "32")) ** 2    # must match the library build (include/rt_b200.h)
 
 
@@ -54,7 +57,7 @@ class rt_camera(C.Structure):
 
 class rt_scene(C.Structure):
     _fields_ = [("camera", rt_camera), ("num_geometries", C.c_int32), ("num_materials", C.c_int32),
-                ("num_lights", C.c_int32), ("reserved_", C.c_int32), ("num_faces", C.c_int64),
+                ("num_lights", C.c_int32), ("flags", C.c_uint32), ("num_faces", C.c_int64),
                 ("geometries", C.POINTER(rt_geometry)), ("materials", C.POINTER(rt_material)),
                 ("lights", C.POINTER(rt_light)), ("face_points", C.POINTER(C.c_double)),
                 ("face_normals", C.POINTER(C.c_double))]
@@ -63,7 +66,7 @@ class rt_scene(C.Structure):
 class rt_params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bounce_depth", C.c_int32),
                 ("intersection_only", C.c_int32), ("tile_rank", C.c_int32), ("tile_world", C.c_int32),
-                ("flags", C.c_uint32), ("samples", C.c_int32)]
+                ("flags", C.c_uint32), ("samples", C.c_int32), ("n_gpus", C.c_int32), ("reserved_", C.c_int32 * 3)]
 
 
 class rt_stats(C.Structure):
@@ -88,6 +91,7 @@ RT_SYMBOLS = [
     "rt_render_device", "rt_render_device_rgb8", "rt_tile_count", "rt_tile_count_total", "rt_tile_count_max",
     "rt_unpack_tiles_rgb8", "rt_unpack_tiles", "rt_primary_ids", "rt_cast_rays", "rt_get_stats",
     "rt_microbench_gather", "rt_scene_device_bytes", "rt_intersection_max", "rt_divide_device",
+    "rt_shared_frame_create", "rt_shared_frame_open", "rt_shared_frame_close", "rt_microbench_node_walk",
 ]
 
 _rt = None
@@ -131,6 +135,10 @@ def load_rt() -> C.CDLL:
         lib.rt_intersection_max.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.rt_divide_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
         lib.rt_scene_device_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.rt_shared_frame_create.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+        lib.rt_shared_frame_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.rt_shared_frame_close.argtypes = [C.c_void_p, C.c_void_p]
+        lib.rt_microbench_node_walk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _rt = lib
     return _rt
 
@@ -241,9 +249,10 @@ def flat_arrays(flat) -> dict:
 
 
 def make_params(width, height, bounce_depth=10, intersection_only=False, tile_rank=0, tile_world=1, flags=0,
-                samples=0) -> rt_params:
+                samples=0, n_gpus=0) -> rt_params:
     p = rt_params()
     p.samples = int(samples)
+    p.n_gpus = int(n_gpus)
     p.width, p.height, p.bounce_depth = int(width), int(height), int(bounce_depth)
     p.intersection_only = int(bool(intersection_only))
     p.tile_rank, p.tile_world, p.flags = int(tile_rank), int(tile_world), int(flags)
@@ -272,14 +281,14 @@ class Renderer:
         self._scene_keepalive = scene
         self._check(self.lib.rt_scene_upload(self._h, C.cast(flat, C.c_void_p)), "rt_scene_upload")
 
-    def render(self, width, height, bounce_depth=10, intersection_only=False, flags=0, samples=0) -> np.ndarray:
-        p = make_params(width, height, bounce_depth, intersection_only, flags=flags, samples=samples)
+    def render(self, width, height, bounce_depth=10, intersection_only=False, flags=0, samples=0, n_gpus=0) -> np.ndarray:
+        p = make_params(width, height, bounce_depth, intersection_only, flags=flags, samples=samples, n_gpus=n_gpus)
         out = np.empty((height, width, 3), dtype=np.float64)
         self._check(self.lib.rt_render(self._h, C.byref(p), _ptr(out), None, None), "rt_render")
         return out
 
-    def render_rgb8(self, width, height, bounce_depth=10, intersection_only=False, flags=0, out=None) -> np.ndarray:
-        p = make_params(width, height, bounce_depth, intersection_only, flags=flags)
+    def render_rgb8(self, width, height, bounce_depth=10, intersection_only=False, flags=0, out=None, n_gpus=0) -> np.ndarray:
+        p = make_params(width, height, bounce_depth, intersection_only, flags=flags, n_gpus=n_gpus)
         if out is None:
             out = np.empty((height, width, 3), dtype=np.uint8)
         self._check(self.lib.rt_render_rgb8(self._h, C.byref(p), _ptr(out), None, None), "rt_render_rgb8")
@@ -311,6 +320,34 @@ class Renderer:
         self._check(self.lib.rt_cast_rays(self._h, n, _ptr(org), _ptr(direction), _ptr(rev), flags, _ptr(geom), _ptr(face),
                                           _ptr(dist), _ptr(point), _ptr(normal)), "rt_cast_rays")
         return geom, face, dist, point, normal
+
+    def render_host_params(self, params: rt_params, host_ptr: int, rgb8=True):
+        """rt_render / rt_render_rgb8 with explicit params and a raw host pointer (pinned or shared memory)."""
+        fn = self.lib.rt_render_rgb8 if rgb8 else self.lib.rt_render
+        self._check(fn(self._h, C.byref(params), C.c_void_p(host_ptr), None, None), "rt_render")
+
+    def shared_frame_create(self, nbytes: int):
+        """-> (device pointer, 64-byte handle) of a frame other processes can open (CUDA IPC)."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self.lib.rt_shared_frame_create(self._h, int(nbytes), C.byref(ptr), handle), "rt_shared_frame_create")
+        return int(ptr.value), handle.raw
+
+    def shared_frame_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.rt_shared_frame_open(self._h, C.create_string_buffer(bytes(handle), 64), C.byref(ptr)),
+                    "rt_shared_frame_open")
+        return int(ptr.value)
+
+    def shared_frame_close(self, ptr: int):
+        self._check(self.lib.rt_shared_frame_close(self._h, C.c_void_p(ptr)), "rt_shared_frame_close")
+
+    def microbench_node_walk(self, lanes=32, visits=64):
+        """-> (wide-node visits per second, bytes per second through the LSU) of the node-walk ceiling probe."""
+        v, b = C.c_double(), C.c_double()
+        self._check(self.lib.rt_microbench_node_walk(self._h, int(lanes), int(visits), C.byref(v), C.byref(b)),
+                    "rt_microbench_node_walk")
+        return float(v.value), float(b.value)
 
     def intersection_max(self) -> float:
         v = C.c_double()

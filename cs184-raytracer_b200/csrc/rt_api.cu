@@ -13,7 +13,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "rt_bvh.h"
@@ -59,7 +62,7 @@ static bool debug_sync() {
         if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "kernel %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
-#define RT_MAX_LEVELS 257     // bounce_depth <= 255 (check_params) -> levels 0..256
+#define RT_MAX_DEPTH 65535     // bounce_depth limit (check_params); counter blocks are allocated per level actually needed
 
 template <typename T>
 struct DevBuf {
@@ -131,10 +134,17 @@ struct rt_context {
     DevBuf<BvhNode> nodes;
     DeviceArena scratch;                    // upload / LBVH-build temporaries
     // render state
-    size_t cap = 0;                         // ray-queue capacity per level
+    size_t cap = 0;                         // ray-queue capacity
     bool cap_fixed = false;                 // pinned by RT_QUEUE_CAP
-    std::vector<DevBuf<double>> qf;         // per level: 9*cap doubles
-    std::vector<DevBuf<int>> qi;            // per level: 2*cap ints
+    // Ray queues come from a pool: a bounce level that fits one chunk hands its queue back as soon as its
+    // k_trace is enqueued, so the levels of a frame ping-pong between two queues (5.1 GB each at 8K) instead of
+    // holding one per level; only levels that are processed in several chunks keep theirs while they recurse.
+    struct RayQueueBuf {
+        DevBuf<double> f;                   // 9*cap doubles
+        DevBuf<int> i;                      // 2*cap ints
+        bool busy = false;
+    };
+    std::vector<RayQueueBuf> qpool;
     DevBuf<double> hf[2];                   // hit queues, 13*(cap/2) each: bounce level l uses buffer l & 1
     DevBuf<int> hi[2];                      // 3*(cap/2) each
     DevBuf<double> hsf;                     // unsorted hit records of the level being traced (hit sorting)
@@ -154,9 +164,22 @@ struct rt_context {
     DevBuf<unsigned long long> ctr;
     DevBuf<unsigned char> staging;          // resolve target for the host-buffer entry points
     // Device counters: [0, CTR_COUNT) legacy block (unused by renders), [CTR_COUNT] the
-    // intersection-only maximum, then one CTR_COUNT block per bounce level (RT_MAX_LEVELS) so
+    // intersection-only maximum, then one CTR_COUNT block per bounce level (levels_alloc of them) so
     // that level l+1 can be enqueued while level l's shadow kernel still reads its own counts.
-    unsigned long long* h_ctr = nullptr;    // pinned: mirror of the level blocks + 2 words for the per-chunk read-back
+    unsigned long long* h_ctr = nullptr;    // pinned: 2 words for the per-chunk read-back, then the mirror of the level blocks
+    int levels_alloc = 0;
+    cudaEvent_t ev_build = nullptr;
+    // ---- multi-GPU inside one process (rt_params.n_gpus > 1): this context drives `peers`, one
+    // sub-context per additional device, each with a replica of the scene (see replicate_scene)
+    std::vector<rt_context*> peers;
+    bool peers_stale = true;                // scene uploaded since the peers were last synchronised
+    size_t used_geoms = 0, used_mats = 0, used_slights = 0, used_alights = 0, used_faces = 0, used_flat = 0,
+           used_all = 0, used_nodes = 0;
+    int worker_rc = RT_OK;                  // result of the last worker-thread section (peers only)
+    std::string worker_err;
+    std::vector<void*> ipc_opened, ipc_created;
+    DevBuf<int> unpack_starts;              // rt_unpack_tiles: per-rank tile-row offsets, kept while the layout is unchanged
+    int unpack_key[3] = {0, 0, 0};          // width, height, world the table was built for
     cudaStream_t copy_stream = nullptr;     // counter read-backs that must not wait for k_shadow
     cudaEvent_t ev_shade = nullptr;
     TileLayout tiles;
@@ -172,6 +195,41 @@ extern "C" {
 
 const char* rt_last_error(void) { return g_error.c_str(); }
 int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+static int init_context(rt_context* ctx, int device, int num_sms) {
+    ctx->device = device;
+    ctx->num_sms = num_sms;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0));
+    CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaEventCreate(&ctx->ev_build));
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->shadow_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) CU(cudaEventCreateWithFlags(&ctx->ev_hq_free[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_shade, cudaEventDisableTiming));
+    // RT_QUEUE_CAP pins the ray-queue capacity (development / tests of the batching logic);
+    // otherwise render_core sizes it from the frame
+    const char* capenv = getenv("RT_QUEUE_CAP");
+    ctx->cap_fixed = capenv != nullptr;
+    ctx->cap = capenv ? (size_t)atoll(capenv) : ((size_t)8 << 20);
+    if (ctx->cap < 2 * RT_TILE_PIXELS) ctx->cap = 2 * RT_TILE_PIXELS;
+    ctx->cap = ctx->cap / (2 * RT_TILE_PIXELS) * (2 * RT_TILE_PIXELS);
+    return RT_OK;
+}
+
+// counter blocks for bounce levels 0..levels-1 (device + pinned mirror)
+static int ensure_levels(rt_context* ctx, int levels) {
+    if (levels <= ctx->levels_alloc) return RT_OK;
+    int want = std::max(levels, 16);
+    if (ctx->h_ctr) { cudaFreeHost(ctx->h_ctr); ctx->h_ctr = nullptr; }
+    ctx->levels_alloc = 0;
+    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * ((size_t)want * CTR_COUNT + 2)));
+    CU(ctx->ctr.ensure(CTR_COUNT + 1 + (size_t)want * CTR_COUNT));
+    ctx->levels_alloc = want;
+    return RT_OK;
+}
 
 int rt_create(int device, rt_context** out) {
     if (!out) return fail(RT_ERR_INVALID, "rt_create: out is NULL");
@@ -192,32 +250,23 @@ int rt_create(int device, rt_context** out) {
         return fail(RT_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100-class; kernels are built for sm_100a only",
                     device, prop.name, prop.major, prop.minor);
     rt_context* ctx = new rt_context();
-    ctx->device = device;
-    ctx->num_sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&ctx->ev0));
-    CU(cudaEventCreate(&ctx->ev1));
-    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * (RT_MAX_LEVELS * CTR_COUNT + 2)));
-    CU(ctx->ctr.ensure(CTR_COUNT + 1 + RT_MAX_LEVELS * CTR_COUNT));
-    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->shadow_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; b++) CU(cudaEventCreateWithFlags(&ctx->ev_hq_free[b], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->ev_shade, cudaEventDisableTiming));
-    // RT_QUEUE_CAP pins the ray-queue capacity (development / tests of the batching logic);
-    // otherwise render_core sizes it from the frame
-    const char* capenv = getenv("RT_QUEUE_CAP");
-    ctx->cap_fixed = capenv != nullptr;
-    ctx->cap = capenv ? (size_t)atoll(capenv) : ((size_t)8 << 20);
-    if (ctx->cap < 2 * RT_TILE_PIXELS) ctx->cap = 2 * RT_TILE_PIXELS;
-    ctx->cap = ctx->cap / (2 * RT_TILE_PIXELS) * (2 * RT_TILE_PIXELS);
+    int rc = init_context(ctx, device, prop.multiProcessorCount);
+    if (rc == RT_OK) rc = ensure_levels(ctx, 16);
+    if (rc != RT_OK) {
+        rt_destroy(ctx);
+        return rc;
+    }
     *out = ctx;
     return RT_OK;
 }
 
 void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
+    for (rt_context* p : ctx->peers) rt_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
+    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (void* p : ctx->ipc_created) cudaFree(p);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->shadow_stream) cudaStreamDestroy(ctx->shadow_stream);
@@ -227,6 +276,7 @@ void rt_destroy(rt_context* ctx) {
     if (ctx->ev_shade) cudaEventDestroy(ctx->ev_shade);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_build) cudaEventDestroy(ctx->ev_build);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -268,9 +318,11 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     CU(cudaSetDevice(ctx->device));
     ctx->have_scene = false;
     ctx->sort_ok = false;
+    ctx->peers_stale = true;
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev0, st));
     int launches = 0;
+    const bool faces_on_device = (s->flags & RT_SCENE_FACES_ON_DEVICE) != 0;
 
     // ---- host-side conversion of the small arrays ----
     const int ng = s->num_geometries;
@@ -387,38 +439,43 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     // LBVH, except giants (floors) that would bloat its upper levels.
     std::vector<int> flat_codes, bvh_codes;
     const size_t kFlatMax = 64, kGiantMax = 16;
+    // world-space extent of every sphere / `tri` (few: host side)
+    std::vector<double> ext(simple_codes.size(), 0.0), pabs(simple_codes.size(), 0.0);
+    double ulo[3] = {1e300, 1e300, 1e300}, uhi[3] = {-1e300, -1e300, -1e300};
+    for (size_t k = 0; k < simple_codes.size(); k++) {
+        int code = simple_codes[k], gi = code & PRIM_INDEX_MASK;
+        const rt_geometry& g = s->geometries[gi];
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        auto grow = [&](const double* p) {
+            for (int a = 0; a < 3; a++) {
+                double w = g.fwd[4 * a] * p[0] + g.fwd[4 * a + 1] * p[1] + g.fwd[4 * a + 2] * p[2] + g.fwd[4 * a + 3];
+                lo[a] = std::fmin(lo[a], w);
+                hi[a] = std::fmax(hi[a], w);
+            }
+        };
+        if (g.type == RT_GEOM_SPHERE) {
+            for (int c = 0; c < 8; c++) {
+                double p[3] = {g.center[0] + ((c & 1) ? g.radius : -g.radius),
+                               g.center[1] + ((c & 2) ? g.radius : -g.radius),
+                               g.center[2] + ((c & 4) ? g.radius : -g.radius)};
+                grow(p);
+            }
+        } else {
+            double six[18];
+            if (faces_on_device) CU(cudaMemcpy(six, s->face_points + 9 * g.first_face, sizeof(six), cudaMemcpyDeviceToHost));
+            else memcpy(six, s->face_points + 9 * g.first_face, sizeof(six));
+            for (int v = 0; v < 6; v++) grow(six + 3 * v);
+        }
+        for (int a = 0; a < 3; a++) {
+            ext[k] = std::fmax(ext[k], hi[a] - lo[a]);
+            pabs[k] = std::fmax(pabs[k], std::fmax(std::fabs(lo[a]), std::fabs(hi[a])));
+            ulo[a] = std::fmin(ulo[a], lo[a]);
+            uhi[a] = std::fmax(uhi[a], hi[a]);
+        }
+    }
     if (simple_codes.size() <= kFlatMax) {
         flat_codes = simple_codes;
     } else {
-        std::vector<double> ext(simple_codes.size(), 0.0);
-        double ulo[3] = {1e300, 1e300, 1e300}, uhi[3] = {-1e300, -1e300, -1e300};
-        for (size_t k = 0; k < simple_codes.size(); k++) {
-            int code = simple_codes[k], gi = code & PRIM_INDEX_MASK;
-            const rt_geometry& g = s->geometries[gi];
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            auto grow = [&](const double* p) {
-                for (int a = 0; a < 3; a++) {
-                    double w = g.fwd[4 * a] * p[0] + g.fwd[4 * a + 1] * p[1] + g.fwd[4 * a + 2] * p[2] + g.fwd[4 * a + 3];
-                    lo[a] = std::fmin(lo[a], w);
-                    hi[a] = std::fmax(hi[a], w);
-                }
-            };
-            if (g.type == RT_GEOM_SPHERE) {
-                for (int c = 0; c < 8; c++) {
-                    double p[3] = {g.center[0] + ((c & 1) ? g.radius : -g.radius),
-                                   g.center[1] + ((c & 2) ? g.radius : -g.radius),
-                                   g.center[2] + ((c & 4) ? g.radius : -g.radius)};
-                    grow(p);
-                }
-            } else {
-                for (int v = 0; v < 6; v++) grow(s->face_points + 9 * g.first_face + 3 * v);
-            }
-            for (int a = 0; a < 3; a++) {
-                ext[k] = std::fmax(ext[k], hi[a] - lo[a]);
-                ulo[a] = std::fmin(ulo[a], lo[a]);
-                uhi[a] = std::fmax(uhi[a], hi[a]);
-            }
-        }
         double uext = 0;
         for (int a = 0; a < 3; a++) uext = std::fmax(uext, uhi[a] - ulo[a]);
         for (size_t k = 0; k < simple_codes.size(); k++) {
@@ -426,6 +483,12 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
             else bvh_codes.push_back(simple_codes[k]);
         }
     }
+    // Every point a ray of a render can start from is the camera eye or lies on a primitive: the largest
+    // |coordinate| of the eye and of the primitives OUTSIDE the LBVH (those inside are measured on the device)
+    // scales the LBVH box padding, see slab1() in rt_device.cuh.
+    double origin_abs = 0;
+    for (int k = 0; k < 3; k++) origin_abs = std::fmax(origin_abs, std::fabs(s->camera.eye[k]));
+    for (size_t k = 0; k < simple_codes.size(); k++) origin_abs = std::fmax(origin_abs, pabs[k]);
     const int n_simple_in_bvh = (int)bvh_codes.size();       // bvh_codes: the simple part only (host copy)
     const size_t n_bvh = (size_t)n_simple_in_bvh + n_mesh_faces;
     for (FaceOwner& o : owners)
@@ -472,12 +535,17 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     }
     if (s->num_faces) {
         const size_t nf = (size_t)s->num_faces;
-        double* raw_p = ctx->scratch.take<double>(nf * 9);
-        double* raw_n = ctx->scratch.take<double>(nf * 9);
+        const double *raw_p = s->face_points, *raw_n = s->face_normals;
+        if (!faces_on_device) {
+            double* up = ctx->scratch.take<double>(nf * 9);
+            double* un = ctx->scratch.take<double>(nf * 9);
+            if (!up || !un) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
+            CU(cudaMemcpyAsync(up, s->face_points, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(un, s->face_normals, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+            raw_p = up; raw_n = un;
+        }
         FaceOwner* d_owners = ctx->scratch.take<FaceOwner>(owners.size() ? owners.size() : 1);
-        if (!raw_p || !raw_n || !d_owners) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
-        CU(cudaMemcpyAsync(raw_p, s->face_points, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(raw_n, s->face_normals, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, st));
+        if (!d_owners) return fail(RT_ERR_OOM, "upload scratch arena exhausted");
         if (!owners.empty())
             CU(cudaMemcpyAsync(d_owners, owners.data(), sizeof(FaceOwner) * owners.size(), cudaMemcpyHostToDevice, st));
         k_pack_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>((long long)nf, raw_p, raw_n, d_owners, (int)owners.size(),
@@ -513,19 +581,20 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     CU(cudaEventRecord(ctx->ev1, st));
 
     // ---- LBVH ----
-    cudaEvent_t evb;
-    CU(cudaEventCreate(&evb));
+    cudaEvent_t evb = ctx->ev_build;
     size_t node_count = 0;
+    S.origin_limit = 3.0e38f;
     if (n_bvh >= 2) {
-        float eye_abs = 0.f;
-        for (int k = 0; k < 3; k++) eye_abs = fmaxf(eye_abs, (float)fabs(s->camera.eye[k]));
+        const float extra_abs = std::nextafter((float)origin_abs, INFINITY);
         char err[256] = "";
         float cb[6] = {0, 0, 0, 0, 0, 0};
+        float pad_scale = 0.f;
         CU(ctx->nodes.ensure(n_bvh + 2));
-        int brc = build_lbvh(S, ctx->bvh_prims.p, group_first_code, (int)n_bvh, group_sizes, 2, eye_abs, st,
-                             ctx->scratch, ctx->nodes.p, &node_count, &launches, err, sizeof(err), cb);
+        int brc = build_lbvh(S, ctx->bvh_prims.p, group_first_code, (int)n_bvh, group_sizes, 2, extra_abs, st,
+                             ctx->scratch, ctx->nodes.p, &node_count, &launches, err, sizeof(err), cb, nullptr, &pad_scale);
         ctx->scratch.reset();
-        if (brc != RT_OK) { cudaEventDestroy(evb); return fail(brc, "LBVH build: %s", err); }
+        if (brc != RT_OK) return fail(brc, "LBVH build: %s", err);
+        S.origin_limit = pad_scale;
         float ext = 0.f;
         for (int a = 0; a < 3; a++) ext = fmaxf(ext, cb[3 + a] - cb[a]);
         ctx->sort_ok = ext > 0.f && std::isfinite(ext);
@@ -538,13 +607,15 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
     float ms0 = 0, ms1 = 0;
     cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1);
     cudaEventElapsedTime(&ms1, ctx->ev1, evb);
-    cudaEventDestroy(evb);
+    ctx->used_geoms = (size_t)ng; ctx->used_mats = hm.size(); ctx->used_slights = hsl.size(); ctx->used_alights = hal.size();
+    ctx->used_faces = (size_t)s->num_faces; ctx->used_flat = flat_codes.size(); ctx->used_all = n_all;
+    ctx->used_nodes = node_count ? n_bvh + 2 : 0;
     ctx->node_bytes = sizeof(BvhNode) * node_count;
     ctx->face_bytes = sizeof(double2) * RT_FACE_D2 * 2 * (size_t)s->num_faces;
     ctx->stats.scene_bytes_h2d = sizeof(DGeom) * hg.size() + sizeof(DMat) * hm.size() +
                                  sizeof(DLight) * (hsl.size() + hal.size()) +
                                  sizeof(int) * (flat_codes.size() + 2 * simple_codes.size() + bvh_codes.size()) +
-                                 sizeof(FaceOwner) * owners.size() + (size_t)s->num_faces * (2 * 72);
+                                 sizeof(FaceOwner) * owners.size() + (faces_on_device ? 0 : (size_t)s->num_faces * (2 * 72));
     ctx->stats.ms_upload = ms0;
     ctx->stats.ms_build = ms1;
     ctx->stats.kernel_launches = (uint64_t)launches;
@@ -569,7 +640,29 @@ struct RenderJob {
     int* ids_face;
     unsigned long long* maxbits;   // intersection-only
     uint64_t launches;
+    int max_level;                 // deepest bounce level that held rays
+    // progress reporting (Scene::ProgressHandler, src/scene.cpp:41-47: every 100 ms on the calling thread)
+    rt_progress_fn cb;
+    void* cb_user;
+    long long px_total, px_before_batch, px_batch, px_reported;
+    std::chrono::steady_clock::time_point last_cb;
 };
+
+// Called wherever the host has just synchronised with the device anyway (the per-level counter read-back):
+// reports at most every 100 ms, like the reference's polling loop.  `frac` = share of the current batch that
+// is behind us (estimated from the bounce level reached); the reported value never decreases and stays below
+// the total until the final (total, total) call of render_core.
+void progress_tick(RenderJob& J, double frac) {
+    if (!J.cb) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (now - J.last_cb < std::chrono::milliseconds(100)) return;
+    long long done = J.px_before_batch + (long long)(frac * (double)J.px_batch);
+    done = std::min(done, J.px_total - 1);
+    if (done <= J.px_reported) return;
+    J.px_reported = done;
+    J.last_cb = now;
+    J.cb((int)done, (int)J.px_total, J.cb_user);
+}
 
 // RT_FLAG_TIME_KERNELS: a (start, stop) event pair around one launch of kernel class `cls`.
 struct LaunchTimer {
@@ -598,24 +691,31 @@ struct LaunchTimer {
     }
 };
 
-RayQ level_queue(rt_context* ctx, int level) {
+RayQ pool_queue(rt_context* ctx, int qi) {
     RayQ q;
-    q.f = ctx->qf[(size_t)level].p;
-    q.pixel = ctx->qi[(size_t)level].p;
-    q.meta = ctx->qi[(size_t)level].p + ctx->cap;
+    q.f = ctx->qpool[(size_t)qi].f.p;
+    q.pixel = ctx->qpool[(size_t)qi].i.p;
+    q.meta = ctx->qpool[(size_t)qi].i.p + ctx->cap;
     q.cap = ctx->cap;
     return q;
 }
 
-int ensure_level(rt_context* ctx, int level) {
-    if ((int)ctx->qf.size() <= level) {
-        ctx->qf.resize((size_t)level + 1);
-        ctx->qi.resize((size_t)level + 1);
+// A free ray queue of the current capacity (allocated on first use, kept across frames).
+int acquire_queue(rt_context* ctx, int* out) {
+    int qi = -1;
+    for (size_t k = 0; k < ctx->qpool.size(); k++)
+        if (!ctx->qpool[k].busy) { qi = (int)k; break; }
+    if (qi < 0) {
+        ctx->qpool.emplace_back();
+        qi = (int)ctx->qpool.size() - 1;
     }
-    CU(ctx->qf[(size_t)level].ensure(9 * ctx->cap));
-    CU(ctx->qi[(size_t)level].ensure(2 * ctx->cap));
+    CU(ctx->qpool[(size_t)qi].f.ensure(9 * ctx->cap));
+    CU(ctx->qpool[(size_t)qi].i.ensure(2 * ctx->cap));
+    ctx->qpool[(size_t)qi].busy = true;
+    *out = qi;
     return RT_OK;
 }
+void release_queue(rt_context* ctx, int qi) { ctx->qpool[(size_t)qi].busy = false; }
 
 template <bool BRUTE, bool COUNT>
 int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h, unsigned long long* lc) {
@@ -637,10 +737,12 @@ int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc, cudaStrea
     return RT_OK;
 }
 
-// Process n rays sitting in level `level`'s queue (and, recursively, everything they spawn).
-int process_level(RenderJob& J, int level, size_t n) {
+// Process the n rays sitting in ray queue `qi` (bounce level `level`) and, recursively, everything they
+// spawn.  The queue is handed back to the pool once its last chunk has been traced.
+int process_level(RenderJob& J, int level, int qi, size_t n) {
     rt_context* ctx = J.ctx;
     const size_t maxchunk = ctx->cap / 2;
+    J.max_level = std::max(J.max_level, level);
     // Hit queue b = level & 1.  k_shadow runs on its own stream: it only reads this level's hit
     // queue and counters and adds into the framebuffer, so the next level's k_trace / k_shade
     // (other hit buffer, other counters) run beside it and fill the tail of the small launches.
@@ -656,10 +758,13 @@ int process_level(RenderJob& J, int level, size_t n) {
     const bool ids_only = J.ids_geom != nullptr;
     // this level's counter block (CTR_HITS / CTR_NEXT are reset per chunk, the rest accumulate)
     unsigned long long* lc = ctx->ctr.p + (CTR_COUNT + 1) + (size_t)level * CTR_COUNT;
-    unsigned long long* h_pair = ctx->h_ctr + (size_t)RT_MAX_LEVELS * CTR_COUNT;
+    unsigned long long* h_pair = ctx->h_ctr;
+    const RayQ q = pool_queue(ctx, qi);
+    bool q_released = false;
+    auto release_q = [&]() { if (!q_released) { release_queue(ctx, qi); q_released = true; } };
     for (size_t off = 0; off < n; off += maxchunk) {
         const int m = (int)std::min(maxchunk, n - off);
-        RayQ q = level_queue(ctx, level);
+        const bool last_chunk = off + maxchunk >= n;
         if (J.overlap && ctx->hq_pending[b]) {
             // the shadow kernel that read this hit buffer (and possibly this counter block) last
             CU(cudaStreamWaitEvent(J.st, ctx->ev_hq_free[b], 0));
@@ -677,7 +782,9 @@ int process_level(RenderJob& J, int level, size_t n) {
         }
         if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, ht, lc) : launch_trace<true, false>(J, q, off, m, ht, lc);
         else lrc = J.count ? launch_trace<false, true>(J, q, off, m, ht, lc) : launch_trace<false, false>(J, q, off, m, ht, lc);
-        if (lrc != RT_OK) return lrc;
+        if (lrc != RT_OK) { release_q(); return lrc; }
+        // everything enqueued on J.st from here on runs after this k_trace, the last reader of the queue
+        if (last_chunk) release_q();
         if (ids_only) continue;
         const int* sorted_order = nullptr;
         if (sorting) {
@@ -703,11 +810,12 @@ int process_level(RenderJob& J, int level, size_t n) {
             continue;
         }
         const bool last_level = level >= J.p->bounce_depth;
-        RayQ next = q;
+        int nqi = -1;
+        RayQ next = q;                          // unused by k_shade on the last level (depth 0: nothing is spawned)
         if (!last_level) {
-            int rc = ensure_level(ctx, level + 1);
-            if (rc != RT_OK) return rc;
-            next = level_queue(ctx, level + 1);
+            int rc = acquire_queue(ctx, &nqi);
+            if (rc != RT_OK) { release_q(); return rc; }
+            next = pool_queue(ctx, nqi);
         }
         {
             LaunchTimer lt(J, 1);
@@ -724,7 +832,7 @@ int process_level(RenderJob& J, int level, size_t n) {
         if (J.overlap) CU(cudaStreamWaitEvent(sst, ctx->ev_shade, 0));
         if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h, lc, sst) : launch_shadow<true, false>(J, m, h, lc, sst);
         else lrc = J.count ? launch_shadow<false, true>(J, m, h, lc, sst) : launch_shadow<false, false>(J, m, h, lc, sst);
-        if (lrc != RT_OK) return lrc;
+        if (lrc != RT_OK) { if (nqi >= 0) release_queue(ctx, nqi); release_q(); return lrc; }
         if (J.overlap) {
             CU(cudaEventRecord(ctx->ev_hq_free[b], sst));
             ctx->hq_pending[b] = true;
@@ -734,12 +842,17 @@ int process_level(RenderJob& J, int level, size_t n) {
         ctx->stats.hits += nhits;
         ctx->stats.rays_shadow += nhits * (unsigned long long)ctx->S.num_slights;
         ctx->stats.rays_secondary += nnext;
+        if (level == 0) progress_tick(J, 0.5 * (double)(off + (size_t)m) / (double)n);
+        else progress_tick(J, 1.0 - 0.5 / (double)(level + 1));
         if (nnext > 0) {
-            if (last_level) return fail(RT_ERR_CUDA, "internal: rays spawned past the depth limit");
-            int rc = process_level(J, level + 1, (size_t)nnext);
-            if (rc != RT_OK) return rc;
+            if (last_level) { release_q(); return fail(RT_ERR_CUDA, "internal: rays spawned past the depth limit"); }
+            int rc = process_level(J, level + 1, nqi, (size_t)nnext);     // hands nqi back itself
+            if (rc != RT_OK) { release_q(); return rc; }
+        } else if (nqi >= 0) {
+            release_queue(ctx, nqi);
         }
     }
+    release_q();
     return RT_OK;
 }
 
@@ -749,16 +862,19 @@ int check_params(rt_context* ctx, const rt_params* p) {
     if (!ctx->have_scene) return fail(RT_ERR_NO_SCENE, "rt_scene_upload has not been called");
     if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "width and height must be positive");
     if ((long long)p->width * p->height > 2000000000ll) return fail(RT_ERR_INVALID, "frame too large");
-    if (p->bounce_depth < 0 || p->bounce_depth > 255) return fail(RT_ERR_INVALID, "bounce_depth must be in [0,255]");
+    if (p->bounce_depth < 0 || p->bounce_depth > RT_MAX_DEPTH) return fail(RT_ERR_INVALID, "bounce_depth must be in [0,%d]", RT_MAX_DEPTH);
     if (p->tile_world < 1 || p->tile_rank < 0 || p->tile_rank >= p->tile_world)
         return fail(RT_ERR_INVALID, "tile_rank/tile_world out of range");
     if (p->samples < 0 || p->samples > RT_MAX_SAMPLES) return fail(RT_ERR_INVALID, "samples must be in [0,%d]", RT_MAX_SAMPLES);
     if (p->samples > 1 && p->intersection_only) return fail(RT_ERR_INVALID, "supersampling is not defined for intersection_only");
+    if (p->n_gpus < 0 || p->n_gpus > 64) return fail(RT_ERR_INVALID, "n_gpus must be in [0,64]");
+    if (p->n_gpus > 1 && p->tile_world != 1) return fail(RT_ERR_INVALID, "n_gpus > 1 needs tile_world == 1");
     return RT_OK;
 }
 
 // Renders this rank's tiles into ctx->fb (slot order).  ids: also/only record primary hit ids.
-int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_only, rt_progress_fn cb, void* user) {
+int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_only, rt_progress_fn cb, void* user,
+                bool final_cb = true) {
     int rc = check_params(ctx, p);
     if (rc != RT_OK) return rc;
     CU(cudaSetDevice(ctx->device));
@@ -787,8 +903,9 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         CU(ctx->hf[b].ensure(13 * maxchunk));
         CU(ctx->hi[b].ensure(3 * maxchunk));
     }
-    rc = ensure_level(ctx, 0);
+    rc = ensure_levels(ctx, p->bounce_depth + 1);
     if (rc != RT_OK) return rc;
+    for (auto& qb : ctx->qpool) qb.busy = false;
 
     RenderJob J;
     J.ctx = ctx; J.p = p; J.st = st;
@@ -824,8 +941,14 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     ctx->evused = 0;
     J.ids_geom = nullptr; J.ids_face = nullptr;
     J.maxbits = ctx->ctr.p + CTR_COUNT;
-    const size_t n_ctr = CTR_COUNT + 1 + (size_t)RT_MAX_LEVELS * CTR_COUNT;
+    const size_t n_ctr = CTR_COUNT + 1 + (size_t)(p->bounce_depth + 1) * CTR_COUNT;
     J.launches = 0;
+    J.max_level = 0;
+    J.cb = cb; J.cb_user = user;
+    J.px_total = (long long)p->width * p->height;
+    J.px_before_batch = J.px_batch = 0;
+    J.px_reported = -1;
+    J.last_cb = std::chrono::steady_clock::now();
     if (ids_only) {
         CU(ctx->ids_geom.ensure((size_t)nslots));
         CU(ctx->ids_face.ensure((size_t)nslots));
@@ -836,6 +959,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     rt_stats& stats = ctx->stats;
     stats.rays_primary = stats.rays_shadow = stats.rays_secondary = stats.hits = stats.degenerate_rays = 0;
+    stats.ms_readback = 0;
     for (int k = 0; k < 2; k++) stats.nodes_fetched[k] = stats.tris_tested[k] = stats.spheres_tested[k] = 0;
     for (int k = 0; k < 4; k++) { stats.ms_kernel[k] = 0; stats.launches_kernel[k] = 0; }
     CU(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long) * n_ctr, st));
@@ -857,18 +981,21 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     for (long long first = 0; first < nslots; first += slots_per_batch) {
         const long long nslot_batch = std::min<long long>(slots_per_batch, nslots - first);
         const int n = (int)(nslot_batch * sub * sub);
+        int q0 = -1;
+        rc = acquire_queue(ctx, &q0);
+        if (rc != RT_OK) return rc;
         {
             LaunchTimer lt(J, 3);
-            k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, level_queue(ctx, 0), sub);
+            k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, pool_queue(ctx, q0), sub);
         }
         J.launches++;
         LAUNCHED("k_raygen", st);
-        rc = process_level(J, 0, (size_t)n);
+        // progress is counted in pixels of the WHOLE frame: this context's slots stand for tile_world times as many
+        J.px_before_batch = std::min<long long>(first * (long long)p->tile_world, total_px - 1);
+        J.px_batch = std::min<long long>(nslot_batch * (long long)p->tile_world, total_px - 1 - J.px_before_batch);
+        rc = process_level(J, 0, q0, (size_t)n);
         if (rc != RT_OK) return rc;
-        if (cb) {
-            long long done = std::min<long long>((first + nslot_batch) * (long long)p->tile_world, total_px - 1);
-            cb((int)done, (int)total_px, user);
-        }
+        progress_tick(J, 1.0);
     }
     if (overlap) {      // the shadow stream's framebuffer adds must land before anything reads the frame
         CU(cudaEventRecord(ctx->ev_join, ctx->shadow_stream));
@@ -882,8 +1009,8 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         LAUNCHED("k_divide", st);
     }
     CU(cudaEventRecord(ctx->ev1, st));
-    const int used_levels = std::min(p->bounce_depth + 1, RT_MAX_LEVELS);
-    CU(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p + CTR_COUNT + 1, sizeof(unsigned long long) * (size_t)used_levels * CTR_COUNT,
+    const int used_levels = std::min(p->bounce_depth, J.max_level) + 1;
+    CU(cudaMemcpyAsync(ctx->h_ctr + 2, ctx->ctr.p + CTR_COUNT + 1, sizeof(unsigned long long) * (size_t)used_levels * CTR_COUNT,
                        cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
@@ -899,7 +1026,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     stats.rays_primary = (uint64_t)prim * (uint64_t)(sub * sub);
     for (int l = 0; l < used_levels; l++) {
-        const unsigned long long* c = ctx->h_ctr + (size_t)l * CTR_COUNT;
+        const unsigned long long* c = ctx->h_ctr + 2 + (size_t)l * CTR_COUNT;
         stats.degenerate_rays += c[CTR_DEGENERATE];
         stats.nodes_fetched[0] += c[CTR_NODES];
         stats.tris_tested[0] += c[CTR_TRIS];
@@ -916,20 +1043,233 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         stats.ms_kernel[cls] += kms;
         stats.launches_kernel[cls]++;
     }
-    if (cb) cb((int)total_px, (int)total_px, user);
+    if (cb && final_cb) cb((int)total_px, (int)total_px, user);
     return RT_OK;
 }
 
+// Framebuffer (slot order) -> output.  full: `out` is the whole row-major frame and only this context's tiles
+// are stored into it; otherwise the packed tile layout.  remote: `out` is not local device memory (another
+// GPU's frame over NVLink, or pinned host memory over PCIe) -> row-staged word stores for RGB8.
 template <bool QUANT>
-int resolve_to(rt_context* ctx, const rt_params* p, void* d_out, cudaStream_t st) {
+int resolve_to(rt_context* ctx, const rt_params* p, void* out, cudaStream_t st, bool full, bool remote) {
     const long long nslots = (long long)ctx->tiles.ids.size() * RT_TILE_PIXELS;
     if (!nslots) return RT_OK;
     FrameInfo F;
     F.width = p->width; F.height = p->height; F.tiles_x = ctx->tiles.tiles_x; F.tiles_y = ctx->tiles.tiles_y;
     F.tile_ids = ctx->tile_ids.p;
-    k_resolve<QUANT><<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(F, ctx->fb.p, nslots, p->tile_world == 1 ? 1 : 0, d_out);
+#if RT_TILE_W == 32
+    if (QUANT && full && remote) {
+        k_resolve_rgb8_rows<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(F, ctx->fb.p, nslots, (unsigned char*)out);
+        ctx->stats.kernel_launches++;
+        LAUNCHED("k_resolve_rgb8_rows", st);
+        return RT_OK;
+    }
+#endif
+    k_resolve<QUANT><<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(F, ctx->fb.p, nslots, full ? 1 : 0, out);
     ctx->stats.kernel_launches++;
     LAUNCHED("k_resolve", st);
+    return RT_OK;
+}
+
+inline bool full_frame(const rt_params* p) { return p->tile_world == 1 || (p->flags & RT_FLAG_FULL_FRAME) != 0; }
+
+// ---- several GPUs inside one process (rt_params.n_gpus > 1) ---------------------------------------------
+// The context the caller holds drives one sub-context per additional device.  The scene is uploaded (and its
+// LBVH built) once on the primary device and replicated with peer copies; a frame's tiles are interleaved over
+// the devices like over the ranks of a multi-process job, one host thread per device runs the wavefront loop,
+// and every device's resolve kernel stores its tiles straight into the caller's frame.
+
+int ensure_peers(rt_context* ctx, int n) {
+    if ((int)ctx->peers.size() >= n - 1) return RT_OK;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    // RT_MULTI_SAME_DEVICE=1: all sub-contexts on the primary's device (exercises the whole multi-GPU path on a
+    // one-GPU box; no speed-up, of course)
+    const bool same = getenv("RT_MULTI_SAME_DEVICE") != nullptr;
+    if (!same && n > count)
+        return fail(RT_ERR_NO_DEVICE, "n_gpus = %d but only %d CUDA device(s) are visible", n, count);
+    while ((int)ctx->peers.size() < n - 1) {
+        const int k = (int)ctx->peers.size() + 1;
+        const int dev = same ? ctx->device : (ctx->device + k) % count;
+        if (dev != ctx->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, dev, ctx->device));
+            if (!can) return fail(RT_ERR_NO_DEVICE, "device %d cannot access device %d's memory (no NVLink/P2P path)", dev, ctx->device);
+            CU(cudaSetDevice(dev));
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctx->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", dev, ctx->device, cudaGetErrorString(e));
+        }
+        rt_context* pc = new rt_context();
+        int rc = init_context(pc, dev, ctx->num_sms);
+        if (rc == RT_OK) rc = ensure_levels(pc, 16);
+        if (rc != RT_OK) { rt_destroy(pc); cudaSetDevice(ctx->device); return rc; }
+        ctx->peers.push_back(pc);
+        ctx->peers_stale = true;
+    }
+    CU(cudaSetDevice(ctx->device));
+    return RT_OK;
+}
+
+// Device-to-device copy of the primary's scene arrays (faces, LBVH nodes, geometry/material/light tables) into
+// every sub-context: the LBVH is built once, not once per GPU.
+int replicate_scene(rt_context* ctx, int n) {
+    if (!ctx->peers_stale) return RT_OK;
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < n - 1; k++) {
+        rt_context* pc = ctx->peers[(size_t)k];
+        auto copy = [&](auto& dst, const auto& src, size_t count) -> int {
+            using T = std::remove_pointer_t<decltype(src.p)>;
+            CU(cudaSetDevice(pc->device));
+            CU(dst.ensure(count));
+            CU(cudaSetDevice(ctx->device));
+            if (count) CU(cudaMemcpyPeerAsync(dst.p, pc->device, src.p, ctx->device, sizeof(T) * count, ctx->stream));
+            return RT_OK;
+        };
+        int rc;
+        if ((rc = copy(pc->geoms, ctx->geoms, ctx->used_geoms)) != RT_OK) return rc;
+        if ((rc = copy(pc->mats, ctx->mats, ctx->used_mats)) != RT_OK) return rc;
+        if ((rc = copy(pc->slights, ctx->slights, ctx->used_slights)) != RT_OK) return rc;
+        if ((rc = copy(pc->alights, ctx->alights, ctx->used_alights)) != RT_OK) return rc;
+        if ((rc = copy(pc->sph_bound, ctx->sph_bound, ctx->used_geoms)) != RT_OK) return rc;
+        if ((rc = copy(pc->face_pts, ctx->face_pts, ctx->used_faces * RT_FACE_D2)) != RT_OK) return rc;
+        if ((rc = copy(pc->face_nrm, ctx->face_nrm, ctx->used_faces * RT_FACE_D2)) != RT_OK) return rc;
+        if ((rc = copy(pc->flat, ctx->flat, ctx->used_flat)) != RT_OK) return rc;
+        if ((rc = copy(pc->all_prims, ctx->all_prims, ctx->used_all)) != RT_OK) return rc;
+        if ((rc = copy(pc->nodes, ctx->nodes, ctx->used_nodes)) != RT_OK) return rc;
+        pc->S = ctx->S;
+        pc->S.geoms = pc->geoms.p; pc->S.mats = pc->mats.p; pc->S.slights = pc->slights.p; pc->S.alights = pc->alights.p;
+        pc->S.sph_bound = pc->sph_bound.p; pc->S.face_pts = pc->face_pts.p; pc->S.face_nrm = pc->face_nrm.p;
+        pc->S.flat = pc->flat.p; pc->S.all_prims = pc->all_prims.p;
+        pc->S.nodes = ctx->S.nodes ? pc->nodes.p : nullptr;
+        pc->sort_grid = ctx->sort_grid;
+        pc->sort_ok = ctx->sort_ok;
+        pc->node_bytes = ctx->node_bytes; pc->face_bytes = ctx->face_bytes;
+        pc->have_scene = true;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->peers_stale = false;
+    return RT_OK;
+}
+
+// out: the whole row-major frame, addressable from every device (the primary's device memory with peer access
+// enabled, or mapped pinned host memory).  Blocks until every device has stored its tiles.
+template <bool QUANT>
+int render_multi(rt_context* ctx, const rt_params* p, void* out, bool out_is_primary_local, rt_progress_fn cb, void* user) {
+    const int n = p->n_gpus;
+    int rc = ensure_peers(ctx, n);
+    if (rc != RT_OK) return rc;
+    rc = replicate_scene(ctx, n);
+    if (rc != RT_OK) return rc;
+    const bool io = p->intersection_only != 0;
+    std::vector<rt_context*> all;
+    all.push_back(ctx);
+    for (int k = 0; k < n - 1; k++) all.push_back(ctx->peers[(size_t)k]);
+    std::vector<rt_params> sp((size_t)n, *p);
+    for (int k = 0; k < n; k++) { sp[(size_t)k].n_gpus = 1; sp[(size_t)k].tile_rank = k; sp[(size_t)k].tile_world = n; }
+    // a section of work on every device: device 0 on the calling thread (progress callbacks), the others on workers
+    auto on_all = [&](auto&& body) -> int {
+        std::vector<std::thread> th;
+        for (int k = 1; k < n; k++)
+            th.emplace_back([&, k]() {
+                rt_context* c = all[(size_t)k];
+                c->worker_rc = body(k);
+                if (c->worker_rc != RT_OK) c->worker_err = g_error;
+            });
+        int rc0 = body(0);
+        std::string err0 = rc0 != RT_OK ? g_error : std::string();
+        for (auto& t : th) t.join();
+        cudaSetDevice(ctx->device);
+        if (rc0 != RT_OK) return fail(rc0, "%s", err0.c_str());
+        for (int k = 1; k < n; k++)
+            if (all[(size_t)k]->worker_rc != RT_OK)
+                return fail(all[(size_t)k]->worker_rc, "GPU %d: %s", all[(size_t)k]->device, all[(size_t)k]->worker_err.c_str());
+        return RT_OK;
+    };
+    auto resolve = [&](int k) -> int {
+        rt_context* c = all[(size_t)k];
+        const bool remote = !(k == 0 && out_is_primary_local);
+        int r = resolve_to<QUANT>(c, &sp[(size_t)k], out, c->stream, true, remote);
+        if (r != RT_OK) return r;
+        CU(cudaStreamSynchronize(c->stream));
+        return RT_OK;
+    };
+    if (!io) {
+        rc = on_all([&](int k) -> int {
+            rt_context* c = all[(size_t)k];
+            int r = render_core(c, &sp[(size_t)k], c->stream, false, k == 0 ? cb : nullptr, k == 0 ? user : nullptr, /*final_cb=*/false);
+            if (r != RT_OK) return r;
+            return resolve(k);
+        });
+        if (rc != RT_OK) return rc;
+    } else {
+        // --intersection-only divides by the GLOBAL maximum (src/scene.cpp:50-58): render, reduce the per-device
+        // maxima on the host (n doubles), then divide + resolve on every device
+        rc = on_all([&](int k) -> int {
+            rt_context* c = all[(size_t)k];
+            return render_core(c, &sp[(size_t)k], c->stream, false, k == 0 ? cb : nullptr, k == 0 ? user : nullptr, false);
+        });
+        if (rc != RT_OK) return rc;
+        unsigned long long gmax = 0;
+        for (int k = 0; k < n; k++) {
+            unsigned long long bits = 0;
+            CU(cudaSetDevice(all[(size_t)k]->device));
+            CU(cudaMemcpy(&bits, all[(size_t)k]->ctr.p + CTR_COUNT, sizeof(bits), cudaMemcpyDeviceToHost));
+            gmax = std::max(gmax, bits);          // non-negative doubles order like their bit patterns
+        }
+        rc = on_all([&](int k) -> int {
+            rt_context* c = all[(size_t)k];
+            CU(cudaSetDevice(c->device));
+            const size_t nv = c->tiles.ids.size() * RT_TILE_PIXELS * 3;
+            CU(cudaMemcpyAsync(c->ctr.p + CTR_COUNT, &gmax, sizeof(gmax), cudaMemcpyHostToDevice, c->stream));
+            if (nv) {
+                k_divide<<<(unsigned)((nv + 255) / 256), 256, 0, c->stream>>>(c->fb.p, nv, c->ctr.p + CTR_COUNT);
+                LAUNCHED("k_divide", c->stream);
+            }
+            return resolve(k);
+        });
+        if (rc != RT_OK) return rc;
+    }
+    // statistics of the whole frame: counts add up, times are the slowest device's
+    rt_stats& st = ctx->stats;
+    for (int k = 1; k < n; k++) {
+        const rt_stats& o = all[(size_t)k]->stats;
+        st.rays_primary += o.rays_primary; st.rays_shadow += o.rays_shadow; st.rays_secondary += o.rays_secondary;
+        st.degenerate_rays += o.degenerate_rays; st.kernel_launches += o.kernel_launches; st.hits += o.hits;
+        for (int j = 0; j < 2; j++) {
+            st.nodes_fetched[j] += o.nodes_fetched[j]; st.tris_tested[j] += o.tris_tested[j]; st.spheres_tested[j] += o.spheres_tested[j];
+        }
+        for (int j = 0; j < 4; j++) { st.ms_kernel[j] = std::max(st.ms_kernel[j], o.ms_kernel[j]); st.launches_kernel[j] += o.launches_kernel[j]; }
+        st.ms_trace = std::max(st.ms_trace, o.ms_trace);
+    }
+    if (cb) cb(p->width * p->height, p->width * p->height, user);
+    return RT_OK;
+}
+
+// A host pointer the devices can store through (cudaHostAlloc / cudaHostRegister memory)?  Returns its device alias.
+void* mapped_host_alias(void* host) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    return at.devicePointer;
+}
+
+template <bool QUANT>
+int render_device_impl(rt_context* ctx, const rt_params* p, void* d_out, void* stream) {
+    if (!d_out) return fail(RT_ERR_INVALID, "d_out is NULL");
+    int rc = check_params(ctx, p);
+    if (rc != RT_OK) return rc;
+    if (QUANT && p->intersection_only && p->tile_world > 1)
+        return fail(RT_ERR_INVALID, "intersection_only over several ranks needs the FP64 frame: the global maximum is applied after the render "
+                                    "(rt_intersection_max / rt_divide_device)");
+    if (p->n_gpus > 1) return render_multi<QUANT>(ctx, p, d_out, true, nullptr, nullptr);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    rc = render_core(ctx, p, st, false, nullptr, nullptr);
+    if (rc != RT_OK) return rc;
+    // a frame shared with other ranks is remote memory for all of them but (at most) one
+    rc = resolve_to<QUANT>(ctx, p, d_out, st, full_frame(p), p->tile_world > 1 && full_frame(p));
+    if (rc != RT_OK) return rc;
+    CU(cudaStreamSynchronize(st));
     return RT_OK;
 }
 
@@ -938,51 +1278,53 @@ int resolve_to(rt_context* ctx, const rt_params* p, void* d_out, cudaStream_t st
 extern "C" {
 
 int rt_render_device(rt_context* ctx, const rt_params* p, double* d_out, void* stream) {
-    if (!d_out) return fail(RT_ERR_INVALID, "d_out is NULL");
-    cudaStream_t st = stream ? (cudaStream_t)stream : (ctx ? ctx->stream : nullptr);
-    int rc = render_core(ctx, p, st, false, nullptr, nullptr);
-    if (rc != RT_OK) return rc;
-    rc = resolve_to<false>(ctx, p, d_out, st);
-    if (rc != RT_OK) return rc;
-    CU(cudaStreamSynchronize(st));
-    return RT_OK;
+    return render_device_impl<false>(ctx, p, d_out, stream);
 }
-
 int rt_render_device_rgb8(rt_context* ctx, const rt_params* p, uint8_t* d_out, void* stream) {
-    if (!d_out) return fail(RT_ERR_INVALID, "d_out is NULL");
-    cudaStream_t st = stream ? (cudaStream_t)stream : (ctx ? ctx->stream : nullptr);
-    int rc = render_core(ctx, p, st, false, nullptr, nullptr);
-    if (rc != RT_OK) return rc;
-    rc = resolve_to<true>(ctx, p, d_out, st);
-    if (rc != RT_OK) return rc;
-    CU(cudaStreamSynchronize(st));
-    return RT_OK;
+    return render_device_impl<true>(ctx, p, d_out, stream);
 }
 
 static int render_host(rt_context* ctx, const rt_params* p, void* host_out, bool quant, rt_progress_fn cb, void* user) {
     if (!host_out) return fail(RT_ERR_INVALID, "output buffer is NULL");
     int rc = check_params(ctx, p);
     if (rc != RT_OK) return rc;
-    if (p->tile_world != 1) return fail(RT_ERR_INVALID, "host-buffer renders need tile_world == 1 (use rt_render_device*)");
-    rc = render_core(ctx, p, ctx->stream, false, cb, user);
-    if (rc != RT_OK) return rc;
     const size_t px = (size_t)p->width * p->height;
     const size_t bytes = px * 3 * (quant ? 1 : sizeof(double));
+    void* alias = (p->tile_world > 1 || p->n_gpus > 1) ? mapped_host_alias(host_out) : nullptr;
+    if (p->tile_world > 1) {
+        // several processes fill one host frame: each stores its own tiles through its own PCIe link
+        if (!(p->flags & RT_FLAG_FULL_FRAME))
+            return fail(RT_ERR_INVALID, "host-buffer renders with tile_world > 1 need RT_FLAG_FULL_FRAME (or use rt_render_device*)");
+        if (!alias) return fail(RT_ERR_INVALID, "a host frame shared by several ranks must be page-locked (cudaHostRegister / cudaHostAlloc)");
+        if (p->intersection_only) return fail(RT_ERR_INVALID, "intersection_only over several ranks: use rt_render_device + rt_intersection_max");
+        rc = render_core(ctx, p, ctx->stream, false, cb, user);
+        if (rc != RT_OK) return rc;
+        rc = quant ? resolve_to<true>(ctx, p, alias, ctx->stream, true, true) : resolve_to<false>(ctx, p, alias, ctx->stream, true, true);
+        if (rc != RT_OK) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        return RT_OK;
+    }
+    if (p->n_gpus > 1 && alias)      // page-locked caller frame: every device stores its tiles over its own PCIe link
+        return quant ? render_multi<true>(ctx, p, alias, false, cb, user) : render_multi<false>(ctx, p, alias, false, cb, user);
+    CU(cudaSetDevice(ctx->device));
     CU(ctx->staging.ensure(bytes));
-    rc = quant ? resolve_to<true>(ctx, p, ctx->staging.p, ctx->stream) : resolve_to<false>(ctx, p, ctx->staging.p, ctx->stream);
-    if (rc != RT_OK) return rc;
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a));
-    CU(cudaEventCreate(&b));
-    cudaEventRecord(a, ctx->stream);
+    if (p->n_gpus > 1) {             // pageable caller frame: peers store into the primary's staging frame, one copy back
+        rc = quant ? render_multi<true>(ctx, p, ctx->staging.p, true, cb, user) : render_multi<false>(ctx, p, ctx->staging.p, true, cb, user);
+        if (rc != RT_OK) return rc;
+    } else {
+        rc = render_core(ctx, p, ctx->stream, false, cb, user);
+        if (rc != RT_OK) return rc;
+        rc = quant ? resolve_to<true>(ctx, p, ctx->staging.p, ctx->stream, true, false)
+                   : resolve_to<false>(ctx, p, ctx->staging.p, ctx->stream, true, false);
+        if (rc != RT_OK) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = cudaMemcpyAsync(host_out, ctx->staging.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaEventRecord(b, ctx->stream);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, "framebuffer readback: %s", cudaGetErrorString(e));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.ms_readback = ms;
     return RT_OK;
 }
@@ -992,6 +1334,54 @@ int rt_render(rt_context* ctx, const rt_params* p, double* rgb, rt_progress_fn c
 }
 int rt_render_rgb8(rt_context* ctx, const rt_params* p, uint8_t* rgb8, rt_progress_fn cb, void* user) {
     return render_host(ctx, p, rgb8, true, cb, user);
+}
+
+int rt_shared_frame_create(rt_context* ctx, uint64_t bytes, void** d_ptr, unsigned char* handle) {
+    if (!ctx || !d_ptr || !handle || !bytes) return fail(RT_ERR_INVALID, "rt_shared_frame_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RT_SHARED_HANDLE_BYTES, "handle size");
+    CU(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(RT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof(h));
+    ctx->ipc_created.push_back(p);
+    *d_ptr = p;
+    return RT_OK;
+}
+
+int rt_shared_frame_open(rt_context* ctx, const unsigned char* handle, void** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return fail(RT_ERR_INVALID, "rt_shared_frame_open: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_opened.push_back(p);
+    *d_ptr = p;
+    return RT_OK;
+}
+
+int rt_shared_frame_close(rt_context* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return fail(RT_ERR_INVALID, "rt_shared_frame_close: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    for (size_t k = 0; k < ctx->ipc_opened.size(); k++)
+        if (ctx->ipc_opened[k] == d_ptr) {
+            ctx->ipc_opened.erase(ctx->ipc_opened.begin() + (long)k);
+            CU(cudaIpcCloseMemHandle(d_ptr));
+            return RT_OK;
+        }
+    for (size_t k = 0; k < ctx->ipc_created.size(); k++)
+        if (ctx->ipc_created[k] == d_ptr) {
+            ctx->ipc_created.erase(ctx->ipc_created.begin() + (long)k);
+            CU(cudaFree(d_ptr));
+            return RT_OK;
+        }
+    return fail(RT_ERR_INVALID, "rt_shared_frame_close: not a shared frame of this context");
 }
 
 int64_t rt_tile_count(const rt_params* p) {
@@ -1029,9 +1419,13 @@ static int unpack_impl(rt_context* ctx, const rt_params* p, const T* d_packed, T
         }
         starts[(size_t)r * (tiles_y + 1) + tiles_y] = acc;
     }
-    DevBuf<int> d_starts;
-    CU(d_starts.ensure(starts.size()));
-    CU(cudaMemcpyAsync(d_starts.p, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice, st));
+    DevBuf<int>& d_starts = ctx->unpack_starts;
+    if (ctx->unpack_key[0] != p->width || ctx->unpack_key[1] != p->height || ctx->unpack_key[2] != world || !d_starts.p) {
+        CU(d_starts.ensure(starts.size()));
+        CU(cudaMemcpyAsync(d_starts.p, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));          // `starts` is a local
+        ctx->unpack_key[0] = p->width; ctx->unpack_key[1] = p->height; ctx->unpack_key[2] = world;
+    }
     const long long npx = (long long)p->width * p->height;
     k_unpack<T><<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(p->width, p->height, tiles_x, world, rt_tile_count_max(p),
                                                             d_starts.p, tiles_y, d_packed, d_frame);
@@ -1170,6 +1564,33 @@ int rt_microbench_gather(rt_context* ctx, uint64_t array_bytes, int loads_per_th
         if (ms < best) best = ms;
     }
     *gbs = (double)blocks * threads * loads_per_thread * 32.0 / (best * 1e-3) / 1e9;
+    return RT_OK;
+}
+
+int rt_microbench_node_walk(rt_context* ctx, int group, int visits_per_thread, double* visits_per_s, double* bytes_per_s) {
+    if (!ctx || !visits_per_s || visits_per_thread < 1 || group < 1 || group > 32 || (group & (group - 1)))
+        return fail(RT_ERR_INVALID, "rt_microbench_node_walk: bad argument (group must be a power of two <= 32)");
+    if (!ctx->have_scene || !ctx->S.nodes) return fail(RT_ERR_NO_SCENE, "rt_microbench_node_walk needs an uploaded scene with an LBVH");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<float> sink;
+    CU(sink.ensure(1));
+    // the traversal kernels' shape: 64-thread blocks, 16 resident per SM; 8 waves of them
+    const int blocks = ctx->num_sms * RT_SHADOW_MINBLOCKS * 8;
+    k_node_walk<<<blocks, RT_BLOCK, 0, ctx->stream>>>(ctx->S.nodes, visits_per_thread, group, sink.p);   // warm-up
+    LAUNCHED("k_node_walk", ctx->stream);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_node_walk<<<blocks, RT_BLOCK, 0, ctx->stream>>>(ctx->S.nodes, visits_per_thread, group, sink.p);
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (ms < best) best = ms;
+    }
+    const double visits = (double)blocks * RT_BLOCK * (double)visits_per_thread;
+    *visits_per_s = visits / (best * 1e-3);
+    if (bytes_per_s) *bytes_per_s = *visits_per_s * 112.0;
     return RT_OK;
 }
 

@@ -184,12 +184,16 @@ __global__ void k_refit(int n, const int* __restrict__ vals, const float* __rest
 }
 
 // depth of every internal node of one tree (root = 0) by walking the parent chain
-__global__ void k_depth(int n, const int* __restrict__ parent_int, int* __restrict__ depth) {
+__global__ void k_depth(int n, const int* __restrict__ parent_int, int* __restrict__ depth, int* __restrict__ max_depth) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int d = 0;
     for (int p = parent_int[i]; p >= 0; p = parent_int[p]) d++;
     depth[i] = d;
+    // deepest internal node of the whole forest (bounds the traversal stack, see build_lbvh)
+    const unsigned act = __activemask();
+    const int m = __reduce_max_sync(act, d);
+    if ((int)(threadIdx.x & 31) == __ffs(act) - 1) atomicMax(max_depth, m);
 }
 
 // Binary Karras nodes at EVEN depth become 4-wide nodes: each internal child (odd depth) is
@@ -272,7 +276,7 @@ __global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __re
 // otherwise stretch the leaf-level boxes of the mesh over the whole air space.
 int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code, int n, const int* group_sizes, int ngroups,
                float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes, size_t* out_count,
-               int* launches, char* err, int errlen, float* centroid_bounds) {
+               int* launches, char* err, int errlen, float* centroid_bounds, int* out_max_depth, float* out_pad_scale) {
     *out_count = 0;
     float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
     int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
@@ -281,6 +285,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
     const int T = 256;
     const int nblk = (n + T - 1) / T;
     int hb[7];
+    int max_bin_depth = 0;
     float pad_scale = 0.f;
     struct Group { int start, n, root_ref, first_code; float box[6]; };
     Group groups[4];
@@ -296,6 +301,10 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         const int nsuper = K > 1 ? 1 : 0;      // one 4-wide super node joins up to four trees
         total_nodes = (size_t)nsuper;
         for (int g = 0; g < K; g++) total_nodes += (size_t)(groups[g].n > 1 ? groups[g].n - 1 : 0);
+        if (total_nodes > ((size_t)1 << 25)) {      // descend() addresses nodes with a 32-bit byte offset
+            snprintf(err, errlen, "%zu LBVH nodes exceed the limit of 2^25 (4 GB node array)", total_nodes);
+            return RT_ERR_LIMIT;
+        }
         TAKE(plo, float, 3 * (size_t)n);
         TAKE(phi, float, 3 * (size_t)n);
         TAKE(gb, int, 8);
@@ -348,7 +357,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
             k_karras<<<gblk, T, 0, stream>>>(kin, gn, left + gs, right + gs, pint + gs, pleaf + gs);
             k_refit<<<gblk, T, 0, stream>>>(gn, vin, plo, phi, left + gs, right + gs, pint + gs, pleaf + gs,
                                             ilo + 3 * (size_t)gs, ihi + 3 * (size_t)gs, flags + gs);
-            k_depth<<<gblk, T, 0, stream>>>(gn, pint + gs, depth + gs);
+            k_depth<<<gblk, T, 0, stream>>>(gn, pint + gs, depth + gs, gb + 7);
             k_pack_wide<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
                                                 ihi + 3 * (size_t)gs, depth + gs, gb, nodes, (int)node_cursor);
             (*launches) += 4;
@@ -357,8 +366,21 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
             CK(cudaMemcpyAsync(groups[g].box + 3, ihi + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
             node_cursor += (size_t)(gn - 1);
         }
+        CK(cudaMemcpyAsync(&max_bin_depth, gb + 7, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
+        {   // The traversal defers at most 3 siblings per wide level.  Wide levels on a root-to-leaf path: one per
+            // two binary levels (even-depth collapse) + the super node.  The stack (RT_SH_STACK shared + RT_STACK
+            // local entries) must hold them all; Karras trees over 30-bit codes with index-split duplicates stay
+            // far below this, so a scene that does not is rejected instead of silently dropping subtrees.
+            const int wide_levels = max_bin_depth / 2 + 1 + nsuper;
+            if (3 * wide_levels > RT_STACK + RT_SH_STACK) {
+                snprintf(err, errlen, "LBVH is %d binary levels deep: %d deferred entries exceed the traversal stack of %d",
+                         max_bin_depth + 1, 3 * wide_levels, RT_STACK + RT_SH_STACK);
+                return RT_ERR_LIMIT;
+            }
+            if (out_max_depth) *out_max_depth = max_bin_depth;
+        }
         if (nsuper > 0) {
             const float pad = 2e-6f * fmaxf(pad_scale, 1e-30f);
             float lo[3][4], hi[3][4];
@@ -387,6 +409,7 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         }
     }
     *out_count = total_nodes;
+    if (out_pad_scale) *out_pad_scale = pad_scale;
     if (centroid_bounds)
         for (int a = 0; a < 6; a++) centroid_bounds[a] = ord2f(hb[a]);
     return RT_OK;

@@ -42,10 +42,13 @@ inline size_t lbvh_scratch_bytes(size_t n) {
 // group_first_code[g] = first code of group g, all the host side needs to know), groups being consecutive ranges of sizes group_sizes[0..ngroups), and
 // joins them under super nodes so that node 0 is always the root, written to `nodes`
 // (caller-allocated).  n < 2 builds nothing (*out_count = 0).  Temporaries come from `arena`.  extra_abs: largest |coordinate| of ray origins outside the
-// primitives (the camera eye), folded into the box padding.  Returns RT_OK or RT_ERR_CUDA.
+// primitives (the camera eye) and of the primitives kept OUT of the LBVH (flat list), folded into the box padding.
+// Returns RT_OK, RT_ERR_CUDA or RT_ERR_LIMIT (too many nodes / tree deeper than the traversal stack).
 int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code, int n, const int* group_sizes, int ngroups,
                float extra_abs, cudaStream_t stream, DeviceArena& arena, BvhNode* nodes /* >= n + ngroups */,
                size_t* out_count, int* launches, char* err, int errlen,
-               float* centroid_bounds /* [6] or null: min xyz, max xyz of the primitive centroids */);
+               float* centroid_bounds /* [6] or null: min xyz, max xyz of the primitive centroids */,
+               int* out_max_depth /* or null: depth of the deepest internal binary node */,
+               float* out_pad_scale /* or null: the largest |coordinate| the box padding covers */);
 
 }  // namespace rt

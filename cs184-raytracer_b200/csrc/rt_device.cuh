@@ -155,6 +155,11 @@ struct DScene {
     int num_bvh_prims;
     int single_leaf;           // BVH with exactly one primitive: its prim code
     int shadow_mode;           // bit 0: light-major thread mapping of k_shadow
+    // Largest |coordinate| the LBVH box padding was derived for (every primitive's world bounds,
+    // flat ones included, and the camera eye): the FP32 slab test is conservative for ray origins
+    // inside it.  A ray starting further out (only possible through rt_cast_rays) takes the
+    // brute-force path instead.
+    float origin_limit;
 };
 
 // ---- hit bookkeeping ------------------------------------------------------------
@@ -364,11 +369,14 @@ __device__ __forceinline__ FRay make_fray(d3 o, d3 d) {
 }
 // Entry distance of four (already padded) boxes.  near/far planes are picked by the sign of
 // the direction, so t_near <= t_far per axis by construction (x -> fma(x, i, b) is monotone)
-// and the test is  max(t_near, 0) <= min(t_far, tlimit).  Every FP32 rounding in here
-// (conversion of o and d, 1/d, the FMA) moves a plane distance by the equivalent of at most a
-// few 1e-7 x the largest scene coordinate in position, which the box padding (2e-6 x that
-// coordinate, rt_bvh.cu) covers, and tlimit is already rounded up with slack (prune_limit), so
-// rounding can only let MORE boxes through, never fewer.  An empty slot (inverted box) has
+// and the test is  max(t_near, 0) <= min(t_far, tlimit).  The FP32 roundings in here
+// (conversion of o and d, 1/d, b = -o/d, the FMA) move a plane distance by the equivalent of
+// about 2e-7 x (|plane| + |o|) in position.  The box padding (rt_bvh.cu) is 2e-6 x M + 2e-7 x
+// |plane| with M = the largest |coordinate| of ANY primitive of the scene (LBVH or flat list)
+// and of the camera eye, i.e. of every point a render's ray can start from; cast_ray sends rays
+// from further out (DScene::origin_limit, rt_cast_rays only) down the brute-force path.  tlimit
+// is already rounded up with slack (prune_limit), so rounding can only let MORE boxes through,
+// never fewer.  An empty slot (inverted box) has
 // t_near >= +1e30 > t_far <= -1e30 on every axis: never hit.
 // (Explicit __fmaf_rn: this file is compiled with -fmad=false.)
 struct Slab4 {
@@ -455,7 +463,7 @@ struct Stack {
             sts(top, ref, t);
         } else {
             const unsigned k = (top - lim()) / RT_SH_STRIDE(ANYHIT);
-            if (k >= RT_STACK) return;            // 3 pushes per wide level, depth <= 31 wide levels
+            if (k >= RT_STACK) return;            // unreachable: rt_scene_upload rejects trees deeper than the stack (RT_ERR_LIMIT)
             sp.ref[k] = ref;
             if (!ANYHIT) sp.t[k] = t;
         }
@@ -493,7 +501,7 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
                                         WorkCounters& wc) {
     while (cur >= 0) {
         const char* const nb = reinterpret_cast<const char*>(S.nodes);
-        const unsigned off = (unsigned)cur * (unsigned)sizeof(BvhNode);       // node arrays stay below 4 GB (2^25 nodes)
+        const unsigned off = (unsigned)cur * (unsigned)sizeof(BvhNode);       // node arrays stay below 4 GB: rt_scene_upload rejects more than 2^25 nodes
         const float4* pnx = reinterpret_cast<const float4*>(nb + (off + fr.nx));
         const float4* pny = reinterpret_cast<const float4*>(nb + (off + fr.ny));
         const float4* pnz = reinterpret_cast<const float4*>(nb + (off + fr.nz));
@@ -554,13 +562,16 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
 // The closest-hit / any-hit query == Scene::castRay (src/scene.cpp:142-167).
 //   ANYHIT: returns true when an accepted hit with world distance <= limit exists.
 //   BRUTE : ignore the LBVH and test every primitive (debug / parity aid).
-template <bool ANYHIT, bool BRUTE, bool COUNT>
+//   FARCHECK: the origin may lie outside DScene::origin_limit (caller-supplied rays only).
+template <bool ANYHIT, bool BRUTE, bool COUNT, bool FARCHECK = false>
 __device__ __forceinline__ bool cast_ray(const DScene& S, d3 o, d3 d, bool reverse, double limit, Best& best,
                                          WorkCounters& wc, unsigned shbase) {
     best.geom = -1; best.face = -1; best.dobj = 0.0; best.wd = 0.0;
     ObjRay R;
     R.geom = -1; R.box_ok = 1;
-    if (BRUTE) {
+    // origins outside the range the box padding covers (see slab1): no culling for this ray
+    const bool far_origin = FARCHECK && !BRUTE && fmax(fabs(o.x), fmax(fabs(o.y), fabs(o.z))) > (double)S.origin_limit;
+    if (BRUTE || far_origin) {
         for (int i = 0; i < S.num_all; i++)
             if (test_prim<ANYHIT, COUNT>(S, __ldg(S.all_prims + i), o, d, reverse, limit, R, best, wc)) return true;
         return false;

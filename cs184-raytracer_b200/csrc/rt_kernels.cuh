@@ -38,10 +38,12 @@ namespace rt {
 struct RayQ {
     double* f;     // 9 fields: ox oy oz dx dy dz wr wg wb
     int* pixel;    // framebuffer slot, -1 = inactive
-    int* meta;     // depth | inside << 8
+    int* meta;     // remaining depth | fromInside << RT_META_INSIDE_SHIFT
     size_t cap;
     __device__ __forceinline__ double& fld(int k, size_t i) const { return f[(size_t)k * cap + i]; }
 };
+#define RT_META_INSIDE_SHIFT 30
+#define RT_META_DEPTH_MASK ((1 << RT_META_INSIDE_SHIFT) - 1)
 // Hit queue (compacted): P N V W + dist, SoA over `cap` slots.
 struct HitQ {
     double* f;     // 13 fields: P(3) N(3) V(3) W(3) dist
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S
         o = mk3(q.fld(0, i), q.fld(1, i), q.fld(2, i));
         d = mk3(q.fld(3, i), q.fld(4, i), q.fld(5, i));
         meta = q.meta[i];
-        cast_ray<false, BRUTE, COUNT>(S, o, d, (meta >> 8) & 1, 0.0, best, wc, stack_base<false>(sm_stack));
+        cast_ray<false, BRUTE, COUNT>(S, o, d, (meta >> RT_META_INSIDE_SHIFT) & 1, 0.0, best, wc, stack_base<false>(sm_stack));
         if (ids_geom) { ids_geom[pixel] = best.geom; ids_face[pixel] = best.face; }
     }
     bool hit = active && best.geom >= 0;
@@ -263,8 +265,8 @@ __global__ void __launch_bounds__(RT_SHADE_BLOCK) k_shade(DScene S, HitQ src, Hi
         pixel = src.pixel[s];
         int meta = src.meta[s];
         const int geom = src.geom[s];
-        depth = meta & 0xff;
-        inside = (meta >> 8) & 1;
+        depth = meta & RT_META_DEPTH_MASK;
+        inside = (meta >> RT_META_INSIDE_SHIFT) & 1;
         const DMat* m = S.mats + S.geoms[geom].mat;
         if (inside) N = -N;                                   // src/scene.cpp:72-73
         N = inplace_normalize(N);                             // src/scene.cpp:75
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(RT_SHADE_BLOCK) k_shade(DScene S, HitQ src, Hi
         next.fld(3, st) = Td.x; next.fld(4, st) = Td.y; next.fld(5, st) = Td.z;
         next.fld(6, st) = W[0]; next.fld(7, st) = W[1]; next.fld(8, st) = W[2];   // weight 1, not kt
         next.pixel[st] = pixel;
-        next.meta[st] = (depth - 1) | ((inside ^ 1) << 8);
+        next.meta[st] = (depth - 1) | ((inside ^ 1) << RT_META_INSIDE_SHIFT);
     }
     unsigned sr = warp_append(want_r, ctr + CTR_NEXT);
     if (want_r) {
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(RT_SHADE_BLOCK) k_shade(DScene S, HitQ src, Hi
         next.fld(3, sr) = Rd.x; next.fld(4, sr) = Rd.y; next.fld(5, sr) = Rd.z;
         next.fld(6, sr) = W[0] * kr[0]; next.fld(7, sr) = W[1] * kr[1]; next.fld(8, sr) = W[2] * kr[2];
         next.pixel[sr] = pixel;
-        next.meta[sr] = (depth - 1) | (inside << 8);
+        next.meta[sr] = (depth - 1) | (inside << RT_META_INSIDE_SHIFT);
     }
     if (degenerate) atomicAdd(ctr + CTR_DEGENERATE, (unsigned long long)degenerate);
 }
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
             bool lrev = ndl < 0;                              // src/scene.cpp:88
             const double INF = __longlong_as_double(0x7ff0000000000000ll);
             double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
-            int inside = (h.meta[j] >> 8) & 1;
+            int inside = (h.meta[j] >> RT_META_INSIDE_SHIFT) & 1;
             Best best;
             bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc, stack_base<true>(sm_stack));
             if (!occluded) {
@@ -452,6 +454,45 @@ __global__ void k_resolve(FrameInfo F, const double* __restrict__ fb, long long 
     }
 }
 
+// Full-frame RGB8 resolve for a frame that lives on ANOTHER device (peer-mapped, NVLink) or in pinned host
+// memory (PCIe): the stores are what costs there, so one block takes 256 consecutive slots = 8 rows x 32 pixels
+// of one tile, stages the quantised bytes in shared memory and stores them as 4-byte words, 24 per row (96
+// contiguous bytes = three whole sectors per row) instead of three single-byte stores per pixel.
+#if RT_TILE_W == 32
+__global__ void __launch_bounds__(256) k_resolve_rgb8_rows(FrameInfo F, const double* __restrict__ fb, long long nslots,
+                                                            unsigned char* __restrict__ out) {
+    __shared__ __align__(16) unsigned char rows[8][96];
+    const long long slot0 = (long long)blockIdx.x * 256;
+    const long long slot = slot0 + threadIdx.x;
+    int px, py;
+    const bool inside = slot < nslots && slot_to_pixel(F, slot, px, py);
+    {
+        const int j = threadIdx.x, w = j >> 5, l = j & 31;
+        const int x = (w & 3) * 8 + (l & 7), y = (w >> 2) * 4 + (l >> 3);
+        for (int k = 0; k < 3; k++) rows[y][3 * x + k] = inside ? quantize(fb[(size_t)slot * 3 + k]) : 0;
+    }
+    __syncthreads();
+    // pixel of the block's first slot = upper left corner of the 32 x 8 strip
+    int px0, py0;
+    if (slot0 >= nslots) return;
+    slot_to_pixel(F, slot0, px0, py0);
+    if (threadIdx.x < 192) {
+        const int r = threadIdx.x / 24, wd = threadIdx.x % 24;
+        const int y = py0 + r;
+        if (y < F.height) {
+            const size_t base = ((size_t)y * F.width + px0) * 3;
+            if (px0 + 32 <= F.width && (base & 3) == 0) {
+                *reinterpret_cast<unsigned*>(out + base + 4 * wd) = *reinterpret_cast<const unsigned*>(&rows[r][4 * wd]);
+            } else {
+                const int nb = 3 * min(32, F.width - px0);
+                for (int bidx = 4 * wd; bidx < 4 * wd + 4; bidx++)
+                    if (bidx < nb) out[base + bidx] = rows[r][bidx];
+            }
+        }
+    }
+}
+#endif
+
 // Gathered packed tiles (rank-major, each rank padded to max_tiles) -> row-major frame.
 template <typename T>
 __global__ void k_unpack(int width, int height, int tiles_x, int world, long long max_tiles,
@@ -487,7 +528,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_query(DScene S, long long n, const
     if (raw.x == 0 && raw.y == 0 && raw.z == 0) {
         best.geom = -2;
     } else {
-        cast_ray<false, BRUTE, false>(S, o, ray_normalize(raw), reverse ? reverse[i] != 0 : false, 0.0, best, wc, stack_base<false>(sm_stack));
+        cast_ray<false, BRUTE, false, true>(S, o, ray_normalize(raw), reverse ? reverse[i] != 0 : false, 0.0, best, wc, stack_base<false>(sm_stack));
     }
     bool hit = best.geom >= 0;
     if (geom) geom[i] = best.geom;
@@ -508,6 +549,50 @@ __global__ void k_gather_probe(const float4* __restrict__ data, unsigned long lo
         unsigned long long r = x % nrec;
         float4 a = __ldg(data + 2 * r), b = __ldg(data + 2 * r + 1);
         acc += a.x + b.w;
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+// Node-visit ceiling probe (the "measured BVH-node-bandwidth roofline" of BASELINE.json): threads walk the REAL
+// 4-wide node array of the uploaded scene with exactly the loads of descend() — three near planes picked by a
+// direction sign, the three far planes at address ^ 64, the four child references; 7 x 16 B = 112 B per visit — and
+// nothing else: no slab arithmetic, no stack, no primitive tests.  The next node is one of the internal children
+// just loaded (a dependent fetch, like a traversal step), picked by a hash; a node without internal children
+// restarts the walk at the root (the next ray).  `group` consecutive lanes share one path: group = 32 is a fully
+// coherent warp (every load a broadcast), group = 1 gives every lane its own path.  Same block size and
+// occupancy as the traversal kernels.  What it measures is the rate at which the memory system (L1TEX / L2)
+// can feed node visits to this access pattern; a traversal kernel cannot visit nodes faster.
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_node_walk(const BvhNode* __restrict__ nodes, int visits,
+                                                                              int group, float* sink) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned path = t / (unsigned)group;
+    unsigned long long x = (unsigned long long)path * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27;
+    // per-path "direction signs": which half of the node holds the near planes (see FRay)
+    const unsigned nx = (x & 1) ? 64u : 0u, ny = (x & 2) ? 80u : 16u, nz = (x & 4) ? 96u : 32u;
+    float acc = 0.f;
+    int cur = 0;
+    const char* const nb = reinterpret_cast<const char*>(nodes);
+    for (int v = 0; v < visits; v++) {
+        const unsigned off = (unsigned)cur * (unsigned)sizeof(BvhNode);
+        const float4* pnx = reinterpret_cast<const float4*>(nb + (off + nx));
+        const float4* pny = reinterpret_cast<const float4*>(nb + (off + ny));
+        const float4* pnz = reinterpret_cast<const float4*>(nb + (off + nz));
+        const float4 a = __ldg(pnx), b = __ldg(pny), c = __ldg(pnz);
+        const float4 d = __ldg(flip64(pnx)), e = __ldg(flip64(pny)), f = __ldg(flip64(pnz));
+        const int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
+        acc += a.x + b.y + c.z + d.w + e.x + f.y;
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const unsigned r = (unsigned)(x >> 33);
+        // hashed pick among the internal children, first candidate by rotation
+        const int cand[4] = {ref.x, ref.y, ref.z, ref.w};
+        int next = 0;
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {
+            const int cc = cand[(r + k) & 3];
+            next = cc >= 0 ? cc : next;
+        }
+        cur = next;        // 0 (the root) when every child is a leaf or empty
     }
     if (acc == 123.456f) *sink = acc;
 }

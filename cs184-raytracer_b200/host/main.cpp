@@ -57,7 +57,11 @@ int main(int argc, char* argv[]) {
     auto since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
+    // One GPU renders unless --gpus says otherwise: have the driver enumerate (and initialise) only that one —
+    // on an 8-GPU box most of a short run's wall time is CUDA initialisation, not rendering.
+    if (programOptions.gpus_ <= 1 && !std::getenv("CUDA_VISIBLE_DEVICES")) setenv("CUDA_VISIBLE_DEVICES", "0", 0);
     Scene scene;
+    scene.warmDeviceAsync();      // device context creation overlaps the scene parse
     for (const std::string& input : programOptions.inputFilenames_) {
         RTIParser parser(scene);
         try {

@@ -13,7 +13,7 @@ namespace as2 {
 Options programOptions;
 
 namespace {
-enum { kHelp = 1000, kBounceDepth, kIntersectionOnly, kBruteForce, kSamples };
+enum { kHelp = 1000, kBounceDepth, kIntersectionOnly, kBruteForce, kSamples, kGpus };
 const struct option kLongOptions[] = {
     {"help", no_argument, nullptr, kHelp},
     {"output", required_argument, nullptr, 'o'},
@@ -24,6 +24,7 @@ const struct option kLongOptions[] = {
     {"intersection-only", no_argument, nullptr, kIntersectionOnly},
     {"brute-force", no_argument, nullptr, kBruteForce},
     {"aa", required_argument, nullptr, kSamples},
+    {"gpus", required_argument, nullptr, kGpus},
     {nullptr, 0, nullptr, 0},
 };
 
@@ -45,6 +46,9 @@ bool fail(const char* msg) {
 bool Options::parseCommandLine(int argc, char* argv[]) {
     optind = 1;
     int opt;
+    if (const char* g = std::getenv("AS2_GPUS")) {
+        if (!toInt(g, gpus_) || gpus_ < 1 || gpus_ > 64) return fail("AS2_GPUS is invalid.");
+    }
     while ((opt = getopt_long(argc, argv, "t:w:h:o:", kLongOptions, nullptr)) != -1) {
         switch (opt) {
             case 'o': outputFilename_ = optarg; break;
@@ -68,6 +72,10 @@ bool Options::parseCommandLine(int argc, char* argv[]) {
             case kSamples:
                 if (!toInt(optarg, samples_)) return fail("Sample count is invalid.");
                 if (samples_ < 1 || samples_ > 16) return fail("Sample count must be between 1 and 16.");
+                break;
+            case kGpus:
+                if (!toInt(optarg, gpus_)) return fail("GPU count is invalid.");
+                if (gpus_ < 1 || gpus_ > 64) return fail("GPU count must be between 1 and 64.");
                 break;
             case kHelp:
             case '?':

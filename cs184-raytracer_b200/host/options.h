@@ -3,7 +3,8 @@
 // (-h is HEIGHT, not help), -o/--output, --bdepth, --intersection-only, --help,
 // positional .rti files; one global instance `programOptions` that the render path
 // reads, exactly as src/scene.cpp:31,39,50,69 do.  Extra (ours): --brute-force, and --aa N
-// (N x N supersampling, the reference's stated next feature, TODO:2).
+// (N x N supersampling, the reference's stated next feature, TODO:2), --gpus N (render on N GPUs of this
+// box: rt_params.n_gpus; default 1, or the AS2_GPUS environment variable).
 #pragma once
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@ public:
     bool intersectionOnly_ = false;
     bool bruteForce_ = false;      // --brute-force: debug aid, skips the LBVH
     int samples_ = 1;              // --aa N: N x N rays per pixel, averaged (1 = the reference's single centre ray)
+    int gpus_ = 1;                 // --gpus N / AS2_GPUS: GPUs of this box that share the frame's tiles
 };
 
 extern Options programOptions;

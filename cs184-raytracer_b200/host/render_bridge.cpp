@@ -10,10 +10,25 @@ namespace as2 {
 
 Scene::Scene() {}
 Scene::~Scene() {
+    if (warm_.joinable()) warm_.join();
+    if (warmCtx_ && warmCtx_ != ctx_) rt_destroy(warmCtx_);
     if (ctx_) rt_destroy(ctx_);
 }
 
+void Scene::warmDeviceAsync() {
+    if (ctx_ || warm_.joinable()) return;
+    warm_ = std::thread([this]() {
+        warmRc_ = rt_create(-1, &warmCtx_);
+        if (warmRc_ != RT_OK) warmErr_ = rt_last_error();      // rt_last_error() is per thread
+    });
+}
+
 rt_context* Scene::deviceContext() {
+    if (warm_.joinable()) {
+        warm_.join();
+        if (warmRc_ != RT_OK) throw RenderException(warmErr_);
+        ctx_ = warmCtx_;
+    }
     if (!ctx_) {
         if (rt_create(-1, &ctx_) != RT_OK) throw RenderException(rt_last_error());
     }
@@ -38,6 +53,7 @@ rt_params paramsFromOptions(int width, int height) {
     p.tile_world = 1;
     p.flags = programOptions.bruteForce_ ? RT_FLAG_BRUTE_FORCE : 0u;
     p.samples = programOptions.samples_;
+    p.n_gpus = programOptions.gpus_;
     return p;
 }
 }  // namespace

@@ -10,6 +10,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_b200.h"
@@ -203,9 +204,16 @@ public:
     // Flatten the object graph into the ABI descriptor (cached until the scene changes).
     const FlatScene& flatten();
     const rt_stats& lastStats() const { return stats_; }
+    // Starts creating the device context on a helper thread (CUDA initialisation takes far longer than
+    // parsing a small scene); renderScene joins it.  Optional: without it the context is created on first use.
+    void warmDeviceAsync();
 
 private:
     rt_context* deviceContext();
+    std::thread warm_;
+    rt_context* warmCtx_ = nullptr;
+    int warmRc_ = 0;
+    std::string warmErr_;
     bool hasCamera_ = false;
     Camera camera_;
     std::vector<std::unique_ptr<Geometry>> geometries_;

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define RT_OK                0
@@ -40,6 +40,7 @@ extern "C" {
 #define RT_ERR_CUDA         -3   /* a CUDA call failed; see rt_last_error()    */
 #define RT_ERR_NO_SCENE     -4   /* render requested before rt_scene_upload()  */
 #define RT_ERR_OOM          -5   /* device allocation failed                   */
+#define RT_ERR_LIMIT        -6   /* scene exceeds a hard limit of the device layout (see rt_last_error()) */
 
 /* ---- geometry / light kinds ------------------------------------------- */
 #define RT_GEOM_SPHERE 0   /* `sph`  : Sphere            (src/geometry.h:17-23)          */
@@ -108,7 +109,7 @@ typedef struct rt_scene {
     int32_t            num_geometries;
     int32_t            num_materials;
     int32_t            num_lights;
-    int32_t            reserved_;
+    uint32_t           flags;          /* RT_SCENE_*                             */
     int64_t            num_faces;
     const rt_geometry* geometries;     /* [num_geometries]                       */
     const rt_material* materials;      /* [num_materials]                        */
@@ -116,12 +117,21 @@ typedef struct rt_scene {
     const double*      face_points;    /* [num_faces][3 vertices][3], object space */
     const double*      face_normals;   /* [num_faces][3 vertices][3], object space */
 } rt_scene;
+/* face_points / face_normals are DEVICE pointers (memory of the context's device): the upload
+ * packs them in place instead of copying them from the host first.  This is how a caller that
+ * already holds the arrays on the device (e.g. after an NVLink all-gather of per-rank slices
+ * of a scene, one slice per PCIe link) hands them over. */
+#define RT_SCENE_FACES_ON_DEVICE 1u
 
 /* ---- render parameters -------------------------------------------------- */
 #define RT_FLAG_BRUTE_FORCE   1u  /* no LBVH: every ray tests every primitive (parity aid) */
 #define RT_FLAG_COUNT_WORK    2u  /* instrumented build of the same kernels: count nodes /
                                      primitives fetched for the roofline (slower)          */
 #define RT_FLAG_TIME_KERNELS  4u  /* bracket every launch with CUDA events (rt_stats.ms_kernel) */
+#define RT_FLAG_FULL_FRAME   16u  /* tile_world > 1: the output buffer is the WHOLE row-major frame (shared
+                                     by the cooperating ranks: a peer-mapped device buffer, see
+                                     rt_shared_frame_*, or pinned host memory every rank has registered);
+                                     this rank stores only the pixels of its own tiles into it            */
 #define RT_FLAG_SERIAL        8u  /* run a frame's kernels strictly one after another: by default the
                                      shadow kernel of bounce level l runs beside the closest-hit and
                                      shading kernels of level l+1 (their event-bracketed durations
@@ -132,13 +142,20 @@ typedef struct rt_params {
     int32_t  height;             /* programOptions.renderHeight_  (src/options.h:14) */
     int32_t  bounce_depth;       /* programOptions.bounceDepth_   (src/options.h:15) */
     int32_t  intersection_only;  /* programOptions.intersectionOnly_ (src/options.h:16) */
-    int32_t  tile_rank;          /* this process renders tiles with tile % tile_world == tile_rank */
-    int32_t  tile_world;         /* number of cooperating processes/GPUs (>=1)       */
+    int32_t  tile_rank;          /* this context renders the 32x32 tiles with (tx + ty) % tile_world == tile_rank */
+    int32_t  tile_world;         /* number of cooperating processes (>=1), one GPU each */
     uint32_t flags;              /* RT_FLAG_*                                        */
     int32_t  samples;            /* supersampling (the reference's stated next feature, TODO:2): 0 or 1 =
                                     one ray through the pixel centre (src/scene.cpp:28-29); n > 1 = n x n
                                     rays through the centres of an n x n grid inside the pixel, averaged.
                                     n <= RT_MAX_SAMPLES; not with intersection_only / rt_primary_ids      */
+    int32_t  n_gpus;             /* GPUs of THIS process used for the render: 0 or 1 = the
+                                    context's device; N > 1 = the context's device plus the next N-1
+                                    visible devices, tiles interleaved over them, every device resolving
+                                    its tiles straight into the caller's frame (peer stores over NVLink
+                                    for a device frame, its own PCIe link for a pinned host frame).
+                                    Needs tile_world == 1.                                              */
+    int32_t  reserved_[3];
 } rt_params;
 #define RT_MAX_SAMPLES 16
 
@@ -186,7 +203,11 @@ int  rt_scene_upload(rt_context* ctx, const rt_scene* scene);
 
 /* ---- the hot path: Scene::renderScene ----------------------------------- */
 /* rgb: caller-owned double[height][width][3], row 0 = top (src/scene.cpp:26-31),
- * i.e. exactly Scene::RasterImage (src/scene.h:11).  Blocking. */
+ * i.e. exactly Scene::RasterImage (src/scene.h:11).  Blocking.
+ * n_gpus > 1: the frame's tiles are rendered by n_gpus devices; when the buffer is page-locked
+ * (cudaHostAlloc / cudaHostRegister) every device stores its tiles straight into it over its own PCIe link.
+ * tile_world > 1 (several processes filling ONE host frame, e.g. in shared memory): needs RT_FLAG_FULL_FRAME
+ * and a buffer every process has page-locked; this rank stores only its own tiles. */
 int  rt_render(rt_context* ctx, const rt_params* p, double* rgb,
                rt_progress_fn cb, void* user);
 
@@ -197,10 +218,10 @@ int  rt_render_rgb8(rt_context* ctx, const rt_params* p, uint8_t* rgb8,
                     rt_progress_fn cb, void* user);
 
 /* Device-resident variants (no host copies).  d_out is DEVICE memory.
- * When tile_world == 1 the layout is the full row-major frame; otherwise it is
- * this rank's packed tiles (rt_tile_count()*RT_TILE_PIXELS pixels), to be
- * gathered by the caller (NCCL) and unpacked with rt_unpack_tiles*.
- * stream: a cudaStream_t passed as void* (0 = legacy default stream). */
+ * When tile_world == 1 (or RT_FLAG_FULL_FRAME) the layout is the full row-major
+ * frame; otherwise it is this rank's packed tiles (rt_tile_count()*RT_TILE_PIXELS
+ * pixels), to be gathered by the caller (NCCL) and unpacked with rt_unpack_tiles*.
+ * stream: a cudaStream_t passed as void* (0 = the context's own stream). */
 #ifndef RT_TILE_W
 #define RT_TILE_W      32
 #endif
@@ -219,6 +240,18 @@ int     rt_unpack_tiles_rgb8(rt_context* ctx, const rt_params* p, const uint8_t*
                              uint8_t* d_frame, void* stream);
 int     rt_unpack_tiles(rt_context* ctx, const rt_params* p, const double* d_packed,
                         double* d_frame, void* stream);
+
+/* ---- one frame shared by the GPUs of several processes (fused peer-store resolve) ----
+ * Rank 0 creates the frame on its device and publishes the 64-byte handle (any byte
+ * transport: torch.distributed broadcast, a file, a pipe); the other ranks open it and pass
+ * the returned pointer as d_out of rt_render_device[_rgb8] with RT_FLAG_FULL_FRAME: their
+ * resolve kernels then store their tiles directly into rank 0's memory over NVLink, so no
+ * gather collective and no unpack pass exist.  The callers' barrier after the render is the
+ * only synchronisation.  (CUDA IPC; within one process use rt_params.n_gpus instead.) */
+#define RT_SHARED_HANDLE_BYTES 64
+int     rt_shared_frame_create(rt_context* ctx, uint64_t bytes, void** d_ptr, unsigned char* handle /*[64]*/);
+int     rt_shared_frame_open(rt_context* ctx, const unsigned char* handle /*[64]*/, void** d_ptr);
+int     rt_shared_frame_close(rt_context* ctx, void* d_ptr);   /* frees (creator) or unmaps (opener) */
 
 /* --intersection-only across ranks (src/scene.cpp:50-58 divides by the GLOBAL maximum): with
  * tile_world > 1 a render leaves 1/dist^2 un-normalised; the caller max-all-reduces
@@ -246,6 +279,12 @@ int  rt_get_stats(rt_context* ctx, rt_stats* out);
  * 32-byte __ldg gathers over an array of `array_bytes` (use the scene's node-array size),
  * `loads_per_thread` per thread over a full-chip grid.  Returns GB/s in *gbs. */
 int  rt_microbench_gather(rt_context* ctx, uint64_t array_bytes, int loads_per_thread, double* gbs);
+/* Node-visit ceiling of the uploaded scene's LBVH: a kernel with the traversal kernels' launch shape walks the
+ * real 4-wide node array issuing exactly the loads of a traversal step (7 x 16 B per visit, next node = a child
+ * just loaded) and nothing else.  group (1, 2, .. 32): consecutive lanes that share one path (32 = a fully
+ * coherent warp, 1 = every lane its own path).  Returns per-lane wide-node visits per second and the bytes per
+ * second they pull through the LSU (112 B each). */
+int  rt_microbench_node_walk(rt_context* ctx, int group, int visits_per_thread, double* visits_per_s, double* bytes_per_s);
 /* Size in bytes of the LBVH node array and of the face records of the uploaded scene. */
 int  rt_scene_device_bytes(rt_context* ctx, uint64_t* node_bytes, uint64_t* face_bytes);
 

@@ -266,6 +266,83 @@ int ref_render(void* h, int width, int height, int depth, int intersection_only,
     return 0;
 }
 
+// Face index of every primary hit, obtained from the UNMODIFIED reference code: the reference reports only the
+// hit Geometry (Scene::castRay) and, through Geometry::calculateIntersectionNormal, the hit point and normal, but no
+// face number.  For a pixel whose primary ray hits mesh g, every face k of g is put alone into a temporary Mesh
+// (same transform) and handed to the reference's own Mesh code; the first k whose one-face answer equals the full
+// mesh's answer bit for bit (point and normal) is the face the reference picked (its loop keeps the FIRST face of
+// least distance, src/geometry.cpp:108-110).  Our only own logic is a generous object-space bounding-box
+// pre-filter on the hit point that skips faces far away from it.  Spheres report face 0, misses -1.
+int ref_primary_faces(void* h, int width, int height, const int32_t* geom_ids, int32_t* face_ids, int threads) {
+    RefScene* rs = static_cast<RefScene*>(h);
+    Scene& scene = rs->scene;
+    prewarm(scene);
+    const long total = (long)width * height;
+    // per-mesh face boxes (object space), padded
+    std::vector<std::vector<std::array<double, 6>>> boxes(scene.geometries_.size());
+    for (size_t g = 0; g < scene.geometries_.size(); g++) {
+        Mesh* me = dynamic_cast<Mesh*>(scene.geometries_[g].get());
+        if (!me) continue;
+        boxes[g].resize(me->faces_.size());
+        for (size_t k = 0; k < me->faces_.size(); k++) {
+            std::array<double, 6>& b = boxes[g][k];
+            for (int a = 0; a < 3; a++) { b[a] = 1e300; b[3 + a] = -1e300; }
+            for (int v = 0; v < 3; v++)
+                for (int a = 0; a < 3; a++) {
+                    b[a] = std::min(b[a], me->faces_[k].points_[v][a]);
+                    b[3 + a] = std::max(b[3 + a], me->faces_[k].points_[v][a]);
+                }
+            for (int a = 0; a < 3; a++) {
+                double pad = 1e-6 * (std::fabs(b[a]) + std::fabs(b[3 + a]) + 1.0);
+                b[a] -= pad; b[3 + a] += pad;
+            }
+        }
+    }
+    std::atomic<long> next(0);
+    std::atomic<int> bad(0);
+    auto worker = [&]() {
+        Camera& cam = scene.camera_;
+        Mesh one;
+        one.faces_.resize(1);
+        const Geometry* bound = nullptr;
+        while (true) {
+            long start = next.fetch_add(256);
+            if (start >= total) break;
+            long end = std::min(start + 256, total);
+            for (long i = start; i < end; i++) {
+                const int gi = geom_ids[i];
+                face_ids[i] = gi < 0 ? -1 : 0;
+                if (gi < 0) continue;
+                Geometry* g = scene.geometries_[(size_t)gi].get();
+                Mesh* me = dynamic_cast<Mesh*>(g);
+                if (!me) continue;
+                int r = (int)(i / width), c = (int)(i % width);
+                Ray ray = cam.calculateViewingRay((r + 0.5) / height, (c + 0.5) / width);
+                Vector4d P, N;
+                if (!g->calculateIntersectionNormal(ray, P, N, false)) { bad++; face_ids[i] = -2; continue; }
+                if (bound != g) { one.forwardTransform(g->forwardTransform()); bound = g; }
+                Vector4d Po = g->inverseTransform() * P;
+                int found = -2;
+                const auto& bx = boxes[(size_t)gi];
+                for (size_t k = 0; k < me->faces_.size(); k++) {
+                    const std::array<double, 6>& b = bx[k];
+                    if (Po[0] < b[0] || Po[0] > b[3] || Po[1] < b[1] || Po[1] > b[4] || Po[2] < b[2] || Po[2] > b[5]) continue;
+                    one.faces_[0] = me->faces_[k];
+                    Vector4d P1, N1;
+                    if (!one.calculateIntersectionNormal(ray, P1, N1, false)) continue;
+                    if (P1 == P && N1 == N) { found = (int)k; break; }
+                }
+                if (found < 0) bad++;
+                face_ids[i] = found;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 0; i < std::max(1, threads); i++) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+    return bad.load();
+}
+
 // The reference's own Scene::renderScene (only safe when W*H % 2000 == 0).
 int ref_render_stock(void* h, int width, int height, int depth, int intersection_only, int threads,
                      double* rgb) {

@@ -6,7 +6,15 @@
   outputs/                  the reference's nine golden images outputs/image-0N.png
   ref/<scene>_<W>x<H>.npz   outputs of the UNMODIFIED reference hot path (oracle/_ref/libref*.so,
                             built by oracle/Makefile from /root/reference/src): raw FP64
-                            framebuffer, primary-hit geometry ids, castRay call count
+                            framebuffer, primary-hit geometry AND face ids (ref_primary_faces:
+                            the reference's own Mesh code run on one face at a time), castRay
+                            call count
+  ref/synthetic_<W>x<H>.npz the same for the benchmark scene (generated in memory by the host
+                            library, handed to the reference through ref_scene_from_flat)
+  ref/big_<scene>_<W>x<H>.npz  the BASELINE.json configurations at their full sizes (the sizes the
+                            stock reference binary aborts on): ids, ray count, the 8-bit frame
+                            (src/writers.cpp:7 applied to the reference's doubles) and every
+                            8th pixel of the FP64 frame in both directions
 
 The GPU box has no /root/reference; the tests read only what this script wrote.
 Usage: python tests/golden/make_fixtures.py [--ref /root/reference]
@@ -34,11 +42,38 @@ SCENES = {
     "bunny4": ("excess_inputs/bunny4.rti", 10),
 }
 SIZES = [(96, 96), (80, 45)]
+# BASELINE.json configs[1..3] at full size (+ bunny4 at a quarter: 10 minutes of CPU at 4K)
+BIG = [("input-02", 1920, 1080), ("refraction3", 3840, 2160), ("bunny4", 960, 540)]
+SYNTHETIC = (708, 1000, 184)          # grid cells, spheres, seed: bench.py's "synthetic" workload
+SYNTHETIC_SIZES = [(96, 54, 5)]       # width, height, depth
+BIG_STRIDE = 8
+
+
+def quantize(rgb):
+    """(uint8)(clamp(v,0,1)*255.0), truncating: src/writers.cpp:7 in numpy."""
+    v = np.where(1.0 < rgb, 1.0, rgb)
+    v = np.where(v < 0.0, 0.0, v)
+    v = np.where(np.isnan(v), 0.0, v)
+    return (v * 255.0).astype(np.uint8)
+
+
+def render_ref(lib, h, w, hh, depth, threads=8):
+    rgb = np.zeros((hh, w, 3))
+    ids = np.zeros((hh, w), dtype=np.int32)
+    faces = np.zeros((hh, w), dtype=np.int32)
+    sec = C.c_double()
+    calls = C.c_uint64()
+    lib.ref_render(h, w, hh, depth, 0, threads, rgb.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p),
+                   C.byref(sec), C.byref(calls))
+    bad = lib.ref_primary_faces(h, w, hh, ids.ctypes.data_as(C.c_void_p), faces.ctypes.data_as(C.c_void_p), threads)
+    assert bad == 0, f"{bad} primary hits whose face could not be identified"
+    return rgb, ids, faces, int(calls.value)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--no-big", action="store_true", help="skip the full-size BASELINE frames (about a minute of CPU)")
     args = ap.parse_args()
     ref = Path(args.ref)
     for sub, pats in (("inputs", ("*.rti", "*.obj")), ("excess_inputs", ("*.rti", "test.obj", "bunny.obj")),
@@ -62,20 +97,49 @@ def main():
         assert h, (name, err.value)
         h = C.c_void_p(h)
         for (w, hh) in SIZES:
-            rgb = np.zeros((hh, w, 3))
-            ids = np.zeros((hh, w), dtype=np.int32)
-            sec = C.c_double()
-            calls = C.c_uint64()
-            lib.ref_render(h, w, hh, depth, 0, 8, rgb.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p),
-                           C.byref(sec), C.byref(calls))
+            rgb, ids, faces, calls = render_ref(lib, h, w, hh, depth)
             io = np.zeros((hh, w, 3))
             lib.ref_render(h, w, hh, depth, 1, 8, io.ctypes.data_as(C.c_void_p), None, None, None)
             out = HERE / "ref" / f"{name}_{w}x{hh}.npz"
-            np.savez_compressed(out, rgb=rgb, geom=ids, castray_calls=np.uint64(calls.value), depth=depth,
+            np.savez_compressed(out, rgb=rgb, geom=ids, face=faces, castray_calls=np.uint64(calls), depth=depth,
                                 intersection_only=io[..., 0].copy())
-            manifest[out.name] = {"scene": rel, "depth": depth, "castray_calls": int(calls.value),
+            manifest[out.name] = {"scene": rel, "depth": depth, "castray_calls": calls,
                                   "rgb_sha256": hashlib.sha256(rgb.tobytes()).hexdigest()[:16]}
             print(out.name, manifest[out.name])
+        for (bname, w, hh) in BIG:
+            if bname != name or args.no_big:
+                continue
+            rgb, ids, faces, calls = render_ref(lib, h, w, hh, depth)
+            out = HERE / "ref" / f"big_{name}_{w}x{hh}.npz"
+            np.savez_compressed(out, rgb8=quantize(rgb), rgb_sub=rgb[::BIG_STRIDE, ::BIG_STRIDE].copy(), stride=BIG_STRIDE,
+                                geom=ids.astype(np.int16), face=faces, castray_calls=np.uint64(calls), depth=depth)
+            manifest[out.name] = {"scene": rel, "depth": depth, "castray_calls": calls,
+                                  "rgb_sha256": hashlib.sha256(rgb.tobytes()).hexdigest()[:16]}
+            print(out.name, manifest[out.name])
+    # ---- the benchmark scene: host library -> flat descriptor -> the reference's own object graph
+    import importlib.util
+    import sys
+    pkg_dir = ROOT / "cs184-raytracer_b200"
+    spec = importlib.util.spec_from_file_location("cs184_raytracer_b200", pkg_dir / "__init__.py",
+                                                  submodule_search_locations=[str(pkg_dir)])
+    pkg = importlib.util.module_from_spec(spec)
+    sys.modules["cs184_raytracer_b200"] = pkg
+    spec.loader.exec_module(pkg)
+    lib.ref_scene_from_flat.restype = C.c_void_p
+    lib.ref_scene_from_flat.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    host_scene = pkg.HostScene.synthetic(*SYNTHETIC)
+    err = C.create_string_buffer(256)
+    h = lib.ref_scene_from_flat(C.cast(host_scene.flat, C.c_void_p), err, 256)
+    assert h, err.value
+    h = C.c_void_p(h)
+    for (w, hh, depth) in SYNTHETIC_SIZES:
+        rgb, ids, faces, calls = render_ref(lib, h, w, hh, depth)
+        out = HERE / "ref" / f"synthetic_{w}x{hh}.npz"
+        np.savez_compressed(out, rgb=rgb, geom=ids, face=faces, castray_calls=np.uint64(calls), depth=depth,
+                            synthetic=np.array(SYNTHETIC, dtype=np.int64))
+        manifest[out.name] = {"scene": f"synthetic{SYNTHETIC}", "depth": depth, "castray_calls": calls,
+                              "rgb_sha256": hashlib.sha256(rgb.tobytes()).hexdigest()[:16]}
+        print(out.name, manifest[out.name])
     (HERE / "ref" / "MANIFEST.json").write_text(json.dumps(manifest, indent=1, sort_keys=True) + "\n")
 
 

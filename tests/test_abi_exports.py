@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rt_b200.h but not exported"
     assert sorted(pkg.RT_SYMBOLS) == declared
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2
 
 
 def test_host_library_exports(pkg):
