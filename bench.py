@@ -320,12 +320,18 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
         er, en = (int(x) for x in emulate.split("/"))
         p = pkg.make_params(width, height, depth, tile_rank=er, tile_world=en, flags=base_flags)
         config["partition"] = f"EMULATED rank {er} of {en} (its tiles only, no gather)"
+    sub = int(os.environ.get("RT_BENCH_SUB", "0"))         # experiment: k sub-contexts per GPU render this rank's tiles concurrently
+    if sub > 1:
+        os.environ["RT_MULTI_SAME_DEVICE"] = "1"
+        p.n_gpus = sub
+        p.flags |= pkg.RT_FLAG_FULL_FRAME
+        config["partition"] += f"; {sub} concurrent sub-contexts per GPU"
     own_tiles, max_tiles, total_tiles = pkg.tile_counts(p)
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
     shared_ptr = None
     frame = gathered = packed_all = None
     if world == 1 and emulate:
-        out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
+        out = torch.zeros(nbytes if sub > 1 else max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
         out_ptr = out.data_ptr()
     elif world == 1:
         frame = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -132,6 +132,7 @@ struct rt_context {
     DevBuf<int> flat, all_prims, bvh_prims;
     DevBuf<float4> sph_bound;
     DevBuf<BvhNode> nodes;
+    cudaTextureObject_t node_tex = 0;
     DeviceArena scratch;                    // upload / LBVH-build temporaries
     // render state
     size_t cap = 0;                         // ray-queue capacity
@@ -166,7 +167,7 @@ struct rt_context {
     // Device counters: [0, CTR_COUNT) legacy block (unused by renders), [CTR_COUNT] the
     // intersection-only maximum, then one CTR_COUNT block per bounce level (levels_alloc of them) so
     // that level l+1 can be enqueued while level l's shadow kernel still reads its own counts.
-    unsigned long long* h_ctr = nullptr;    // pinned: 2 words for the per-chunk read-back, then the mirror of the level blocks
+    unsigned long long* h_ctr = nullptr;    // pinned: 4 words for the per-chunk read-back, then the mirror of the level blocks
     int levels_alloc = 0;
     cudaEvent_t ev_build = nullptr;
     // ---- multi-GPU inside one process (rt_params.n_gpus > 1): this context drives `peers`, one
@@ -225,7 +226,7 @@ static int ensure_levels(rt_context* ctx, int levels) {
     int want = std::max(levels, 16);
     if (ctx->h_ctr) { cudaFreeHost(ctx->h_ctr); ctx->h_ctr = nullptr; }
     ctx->levels_alloc = 0;
-    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * ((size_t)want * CTR_COUNT + 2)));
+    CU(cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * ((size_t)want * CTR_COUNT + 4)));
     CU(ctx->ctr.ensure(CTR_COUNT + 1 + (size_t)want * CTR_COUNT));
     ctx->levels_alloc = want;
     return RT_OK;
@@ -602,6 +603,22 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
         ctx->sort_grid.scale = ctx->sort_ok ? 1024.f / ext : 0.f;
     }
     S.nodes = node_count ? ctx->nodes.p : nullptr;
+#if RT_TEX_PLANES
+    if (ctx->node_tex) { cudaDestroyTextureObject(ctx->node_tex); ctx->node_tex = 0; }
+    if (node_count) {
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = ctx->nodes.p;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = sizeof(BvhNode) * (n_bvh + 2);
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.readMode = cudaReadModeElementType;
+        CU(cudaCreateTextureObject(&ctx->node_tex, &rd, &td, nullptr));
+    }
+    S.node_tex = ctx->node_tex;
+#endif
     cudaEventRecord(evb, st);
     CU(cudaStreamSynchronize(st));
     float ms0 = 0, ms1 = 0;
@@ -718,9 +735,9 @@ int acquire_queue(rt_context* ctx, int* out) {
 void release_queue(rt_context* ctx, int qi) { ctx->qpool[(size_t)qi].busy = false; }
 
 template <bool BRUTE, bool COUNT>
-int launch_trace(RenderJob& J, RayQ q, size_t off, int n, HitQ h, unsigned long long* lc) {
+int launch_trace(RenderJob& J, RayQ q, size_t off, int n, size_t nfront, HitQ h, unsigned long long* lc) {
     LaunchTimer lt(J, 0);
-    k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, h, lc,
+    k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, nfront, h, lc,
                                                                             J.ids_geom, J.ids_face);
     J.launches++;
     LAUNCHED("k_trace", J.st);
@@ -739,7 +756,7 @@ int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc, cudaStrea
 
 // Process the n rays sitting in ray queue `qi` (bounce level `level`) and, recursively, everything they
 // spawn.  The queue is handed back to the pool once its last chunk has been traced.
-int process_level(RenderJob& J, int level, int qi, size_t n) {
+int process_level(RenderJob& J, int level, int qi, size_t n, size_t nfront) {
     rt_context* ctx = J.ctx;
     const size_t maxchunk = ctx->cap / 2;
     J.max_level = std::max(J.max_level, level);
@@ -771,6 +788,7 @@ int process_level(RenderJob& J, int level, int qi, size_t n) {
             ctx->hq_pending[b] = false;
         }
         CU(cudaMemsetAsync(lc, 0, sizeof(unsigned long long) * 2, J.st));   // CTR_HITS, CTR_NEXT
+        CU(cudaMemsetAsync(lc + CTR_NEXT_T, 0, sizeof(unsigned long long), J.st));
         int lrc;
         const bool sorting = J.sort_bits > 0 && level >= J.sort_first_level && (size_t)m >= J.sort_min_rays && !ids_only && !io;
         HitQ ht = h;               // where k_trace appends
@@ -780,8 +798,8 @@ int process_level(RenderJob& J, int level, int qi, size_t n) {
             ht.geom = ctx->hsi.p + maxchunk;
             ht.meta = ctx->hsi.p + 2 * maxchunk;
         }
-        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, ht, lc) : launch_trace<true, false>(J, q, off, m, ht, lc);
-        else lrc = J.count ? launch_trace<false, true>(J, q, off, m, ht, lc) : launch_trace<false, false>(J, q, off, m, ht, lc);
+        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, nfront, ht, lc) : launch_trace<true, false>(J, q, off, m, nfront, ht, lc);
+        else lrc = J.count ? launch_trace<false, true>(J, q, off, m, nfront, ht, lc) : launch_trace<false, false>(J, q, off, m, nfront, ht, lc);
         if (lrc != RT_OK) { release_q(); return lrc; }
         // everything enqueued on J.st from here on runs after this k_trace, the last reader of the queue
         if (last_chunk) release_q();
@@ -829,6 +847,7 @@ int process_level(RenderJob& J, int level, int qi, size_t n) {
         CU(cudaEventRecord(ctx->ev_shade, J.st));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_shade, 0));
         CU(cudaMemcpyAsync(h_pair, lc, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU(cudaMemcpyAsync(h_pair + 2, lc + CTR_NEXT_T, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (J.overlap) CU(cudaStreamWaitEvent(sst, ctx->ev_shade, 0));
         if (J.brute) lrc = J.count ? launch_shadow<true, true>(J, m, h, lc, sst) : launch_shadow<true, false>(J, m, h, lc, sst);
         else lrc = J.count ? launch_shadow<false, true>(J, m, h, lc, sst) : launch_shadow<false, false>(J, m, h, lc, sst);
@@ -838,7 +857,7 @@ int process_level(RenderJob& J, int level, int qi, size_t n) {
             ctx->hq_pending[b] = true;
         }
         CU(cudaStreamSynchronize(ctx->copy_stream));
-        const unsigned long long nhits = h_pair[CTR_HITS], nnext = h_pair[CTR_NEXT];
+        const unsigned long long nhits = h_pair[CTR_HITS], nrefl = h_pair[CTR_NEXT], nnext = nrefl + h_pair[2];
         ctx->stats.hits += nhits;
         ctx->stats.rays_shadow += nhits * (unsigned long long)ctx->S.num_slights;
         ctx->stats.rays_secondary += nnext;
@@ -846,7 +865,7 @@ int process_level(RenderJob& J, int level, int qi, size_t n) {
         else progress_tick(J, 1.0 - 0.5 / (double)(level + 1));
         if (nnext > 0) {
             if (last_level) { release_q(); return fail(RT_ERR_CUDA, "internal: rays spawned past the depth limit"); }
-            int rc = process_level(J, level + 1, nqi, (size_t)nnext);     // hands nqi back itself
+            int rc = process_level(J, level + 1, nqi, (size_t)nnext, (size_t)nrefl);     // hands nqi back itself
             if (rc != RT_OK) { release_q(); return rc; }
         } else if (nqi >= 0) {
             release_queue(ctx, nqi);
@@ -868,7 +887,8 @@ int check_params(rt_context* ctx, const rt_params* p) {
     if (p->samples < 0 || p->samples > RT_MAX_SAMPLES) return fail(RT_ERR_INVALID, "samples must be in [0,%d]", RT_MAX_SAMPLES);
     if (p->samples > 1 && p->intersection_only) return fail(RT_ERR_INVALID, "supersampling is not defined for intersection_only");
     if (p->n_gpus < 0 || p->n_gpus > 64) return fail(RT_ERR_INVALID, "n_gpus must be in [0,64]");
-    if (p->n_gpus > 1 && p->tile_world != 1) return fail(RT_ERR_INVALID, "n_gpus > 1 needs tile_world == 1");
+    if (p->n_gpus > 1 && p->tile_world != 1 && !(p->flags & RT_FLAG_FULL_FRAME))
+        return fail(RT_ERR_INVALID, "n_gpus > 1 with tile_world > 1 needs RT_FLAG_FULL_FRAME");
     return RT_OK;
 }
 
@@ -993,7 +1013,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         // progress is counted in pixels of the WHOLE frame: this context's slots stand for tile_world times as many
         J.px_before_batch = std::min<long long>(first * (long long)p->tile_world, total_px - 1);
         J.px_batch = std::min<long long>(nslot_batch * (long long)p->tile_world, total_px - 1 - J.px_before_batch);
-        rc = process_level(J, 0, q0, (size_t)n);
+        rc = process_level(J, 0, q0, (size_t)n, (size_t)n);
         if (rc != RT_OK) return rc;
         progress_tick(J, 1.0);
     }
@@ -1010,7 +1030,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     CU(cudaEventRecord(ctx->ev1, st));
     const int used_levels = std::min(p->bounce_depth, J.max_level) + 1;
-    CU(cudaMemcpyAsync(ctx->h_ctr + 2, ctx->ctr.p + CTR_COUNT + 1, sizeof(unsigned long long) * (size_t)used_levels * CTR_COUNT,
+    CU(cudaMemcpyAsync(ctx->h_ctr + 4, ctx->ctr.p + CTR_COUNT + 1, sizeof(unsigned long long) * (size_t)used_levels * CTR_COUNT,
                        cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
@@ -1026,7 +1046,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     stats.rays_primary = (uint64_t)prim * (uint64_t)(sub * sub);
     for (int l = 0; l < used_levels; l++) {
-        const unsigned long long* c = ctx->h_ctr + 2 + (size_t)l * CTR_COUNT;
+        const unsigned long long* c = ctx->h_ctr + 4 + (size_t)l * CTR_COUNT;
         stats.degenerate_rays += c[CTR_DEGENERATE];
         stats.nodes_fetched[0] += c[CTR_NODES];
         stats.tris_tested[0] += c[CTR_TRIS];
@@ -1162,11 +1182,18 @@ int render_multi(rt_context* ctx, const rt_params* p, void* out, bool out_is_pri
     rc = replicate_scene(ctx, n);
     if (rc != RT_OK) return rc;
     const bool io = p->intersection_only != 0;
+    if (io && p->tile_world > 1)
+        return fail(RT_ERR_INVALID, "intersection_only with n_gpus > 1 needs tile_world == 1 (the maximum is reduced inside one process only)");
     std::vector<rt_context*> all;
     all.push_back(ctx);
     for (int k = 0; k < n - 1; k++) all.push_back(ctx->peers[(size_t)k]);
     std::vector<rt_params> sp((size_t)n, *p);
-    for (int k = 0; k < n; k++) { sp[(size_t)k].n_gpus = 1; sp[(size_t)k].tile_rank = k; sp[(size_t)k].tile_world = n; }
+    // device k takes the tiles (tx + ty) % (tile_world * n) == tile_rank + k * tile_world: a refinement of this rank's share
+    for (int k = 0; k < n; k++) {
+        sp[(size_t)k].n_gpus = 1;
+        sp[(size_t)k].tile_rank = p->tile_rank + k * p->tile_world;
+        sp[(size_t)k].tile_world = p->tile_world * n;
+    }
     // a section of work on every device: device 0 on the calling thread (progress callbacks), the others on workers
     auto on_all = [&](auto&& body) -> int {
         std::vector<std::thread> th;

@@ -160,6 +160,9 @@ struct DScene {
     // inside it.  A ray starting further out (only possible through rt_cast_rays) takes the
     // brute-force path instead.
     float origin_limit;
+    // the node array again, as a linear float4 texture (experiment RT_TEX_PLANES: plane loads through the TEX data
+    // pipe, which is separate from the LSU data pipe that limits the traversal kernels)
+    cudaTextureObject_t node_tex;
 };
 
 // ---- hit bookkeeping ------------------------------------------------------------
@@ -392,6 +395,9 @@ __device__ __forceinline__ void slab1(const FRay& r, float nx, float ny, float n
     hit = tn <= tf;
 }
 
+#ifndef RT_TEX_PLANES
+#define RT_TEX_PLANES 0
+#endif
 #define RT_STACK 96
 #ifndef RT_ANYHIT_UNSORTED
 #define RT_ANYHIT_UNSORTED 1
@@ -505,8 +511,18 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
         const float4* pnx = reinterpret_cast<const float4*>(nb + (off + fr.nx));
         const float4* pny = reinterpret_cast<const float4*>(nb + (off + fr.ny));
         const float4* pnz = reinterpret_cast<const float4*>(nb + (off + fr.nz));
+#if RT_TEX_PLANES == 2
+        const float4 nx = tex1Dfetch<float4>(S.node_tex, (int)((off + fr.nx) >> 4)), ny = tex1Dfetch<float4>(S.node_tex, (int)((off + fr.ny) >> 4)),
+                     nz = tex1Dfetch<float4>(S.node_tex, (int)((off + fr.nz) >> 4));
+#else
         const float4 nx = __ldg(pnx), ny = __ldg(pny), nz = __ldg(pnz);
+#endif
+#if RT_TEX_PLANES >= 1
+        const float4 fx = tex1Dfetch<float4>(S.node_tex, (int)(((off + fr.nx) ^ 64u) >> 4)), fy = tex1Dfetch<float4>(S.node_tex, (int)(((off + fr.ny) ^ 64u) >> 4)),
+                     fz = tex1Dfetch<float4>(S.node_tex, (int)(((off + fr.nz) ^ 64u) >> 4));
+#else
         const float4 fx = __ldg(flip64(pnx)), fy = __ldg(flip64(pny)), fz = __ldg(flip64(pnz));
+#endif
         const int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
         if (COUNT) wc.nodes += 4;
         float t0, t1, t2, t3;

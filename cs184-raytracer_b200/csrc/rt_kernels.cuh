@@ -59,6 +59,7 @@ enum {
     CTR_HITS = 0, CTR_NEXT = 1, CTR_DEGENERATE = 2,
     CTR_NODES = 3, CTR_TRIS = 4, CTR_SPHERES = 5,          // closest-hit kernel
     CTR_S_NODES = 6, CTR_S_TRIS = 7, CTR_S_SPHERES = 8,    // shadow kernel
+    CTR_NEXT_T = 9,                                        // refracted children (stored from the END of the next queue)
     CTR_COUNT = 10
 };
 
@@ -145,12 +146,16 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long
 
 // Closest hit for every queued ray; hits are appended (compacted) to the hit queue.
 // ids_geom/ids_face (optional, indexed by framebuffer slot) receive the hit ids.
+// The queue holds its rays in two regions: entries [0, nfront) from the front (camera rays; reflected children) and
+// the rest from the END backwards (refracted children), so a warp is one class of rays from neighbouring origins
+// instead of an interleaving of the two.  Ray number g of the level sits at g (g < nfront) or cap - 1 - (g - nfront).
 template <bool BRUTE, bool COUNT>
-__global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S, RayQ q, size_t off, int n, HitQ h,
+__global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S, RayQ q, size_t off, int n, size_t nfront, HitQ h,
                                                      unsigned long long* ctr, int* ids_geom, int* ids_face) {
     __shared__ __align__(16) unsigned char sm_stack[RT_SH_STACK_BYTES(false)];
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i = off + (size_t)t;
+    const size_t g = off + (size_t)t;
+    const size_t i = g < nfront ? g : q.cap - 1 - (g - nfront);
     bool active = t < n;
     int pixel = active ? q.pixel[i] : -1;
     active = active && pixel >= 0;
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(RT_SHADE_BLOCK) k_shade(DScene S, HitQ src, Hi
             }
         }
     }
-    unsigned st = warp_append(want_t, ctr + CTR_NEXT);
+    unsigned st = (unsigned)next.cap - 1u - warp_append(want_t, ctr + CTR_NEXT_T);
     if (want_t) {
         next.fld(0, st) = P.x; next.fld(1, st) = P.y; next.fld(2, st) = P.z;
         next.fld(3, st) = Td.x; next.fld(4, st) = Td.y; next.fld(5, st) = Td.z;

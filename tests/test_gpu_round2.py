@@ -185,7 +185,7 @@ def test_bounce_depth_above_255(pkg, gpu_renderer, oracle, tmp_path):
     rti = tmp_path / "mirrors.rti"
     rti.write_text("cam 0 0 30  -4 -4 20  4 -4 20  -4 4 20  4 4 20\nlta 0.1 0.1 0.1\nltp 5 8 20 1 1 1\n"
                    "mat 0.05 0.05 0.05 0.2 0.2 0.2 0.3 0.3 0.3 10 0.95 0.95 0.95\n"
-                   "tri -50 -50 -5  50 -50 -5  0 60 -5\ntri -50 -50 40  50 -50 40  0 60 40\n"
+                   "tri -90000 -90000 -5  90000 -90000 -5  0 90000 -5\ntri -90000 -90000 40  90000 -90000 40  0 90000 40\n"
                    "mat 0.1 0.1 0.1 0.8 0.3 0.2 0.5 0.5 0.5 20 0 0 0\nsph 1 -1 10 1.5\n")
     sc = pkg.HostScene.load(rti)
     gpu_renderer.upload(sc)

@@ -4,7 +4,7 @@
 w=$1; shift
 mkdir -p gpurun_out
 for v in "$@"; do
-  RT_B200_LIB_DIR=$PWD/cs184-raytracer_b200/$v python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline --no-e2e \
+  RT_B200_LIB_DIR=$PWD/cs184-raytracer_b200/$v python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --configs none \
       > gpurun_out/ab_${w}_$v.json 2> gpurun_out/ab_${w}_$v.err
   python - "$v" gpurun_out/ab_${w}_$v.json <<'PY'
 import json, sys

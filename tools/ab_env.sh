@@ -3,7 +3,7 @@
 w=$1; var=$2; shift; shift
 mkdir -p gpurun_out
 for v in "$@"; do
-  env $var=$v python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline --no-e2e \
+  env $var=$v python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --configs none \
       > gpurun_out/abenv_${w}_${var}_$v.json 2> gpurun_out/abenv_${w}_${var}_$v.err
   python - "$var=$v" gpurun_out/abenv_${w}_${var}_$v.json <<'PY'
 import json, sys
