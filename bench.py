@@ -620,7 +620,8 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
                     "frame with RT_FLAG_SERIAL, classes add up to ms_serial_frame",
             "node_array_bytes": node_bytes, "face_record_bytes": face_bytes,
             "work_per_step": {"box_tests": cs["nodes_fetched"], "tris": cs["tris_tested"], "spheres": cs["spheres_tested"],
-                              "hits": cs["hits"], "shadow_lights": int(cs["rays_shadow"] // max(cs["hits"], 1))}}
+                              "hits": cs["hits"], "shadow_lights": int(cs["rays_shadow"] // max(cs["hits"], 1)),
+                              "shadow_rays_answered_without_traversal": cs["shadow_rays_culled"]}}
         del scratch
 
     # ---------------- parity of this workload against the stored reference output (rank 0, single-GPU render)

@@ -75,7 +75,7 @@ class rt_stats(C.Structure):
                 ("nodes_fetched", C.c_uint64 * 2), ("tris_tested", C.c_uint64 * 2), ("spheres_tested", C.c_uint64 * 2),
                 ("hits", C.c_uint64), ("ms_kernel", C.c_double * 4), ("launches_kernel", C.c_uint64 * 4),
                 ("ms_upload", C.c_double), ("ms_build", C.c_double), ("ms_trace", C.c_double),
-                ("ms_readback", C.c_double), ("scene_bytes_h2d", C.c_uint64)]
+                ("ms_readback", C.c_double), ("scene_bytes_h2d", C.c_uint64), ("shadow_rays_culled", C.c_uint64)]
 
     def as_dict(self):
         out = {}

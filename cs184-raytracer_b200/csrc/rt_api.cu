@@ -132,7 +132,6 @@ struct rt_context {
     DevBuf<int> flat, all_prims, bvh_prims;
     DevBuf<float4> sph_bound;
     DevBuf<BvhNode> nodes;
-    cudaTextureObject_t node_tex = 0;
     DeviceArena scratch;                    // upload / LBVH-build temporaries
     // render state
     size_t cap = 0;                         // ray-queue capacity
@@ -245,13 +244,16 @@ int rt_create(int device, rt_context** out) {
     }
     if (device >= count) return fail(RT_ERR_NO_DEVICE, "CUDA device %d does not exist (%d present)", device, count);
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(RT_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100-class; kernels are built for sm_100a only",
-                    device, prop.name, prop.major, prop.minor);
+    // three attributes instead of cudaGetDeviceProperties (which queries everything and costs milliseconds of a
+    // short run's start-up)
+    int major = 0, minor = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major < 10)
+        return fail(RT_ERR_NO_DEVICE, "device %d (sm_%d%d) is not sm_100-class; kernels are built for sm_100a only", device, major, minor);
     rt_context* ctx = new rt_context();
-    int rc = init_context(ctx, device, prop.multiProcessorCount);
+    int rc = init_context(ctx, device, sms);
     if (rc == RT_OK) rc = ensure_levels(ctx, 16);
     if (rc != RT_OK) {
         rt_destroy(ctx);
@@ -603,22 +605,6 @@ int rt_scene_upload(rt_context* ctx, const rt_scene* s) {
         ctx->sort_grid.scale = ctx->sort_ok ? 1024.f / ext : 0.f;
     }
     S.nodes = node_count ? ctx->nodes.p : nullptr;
-#if RT_TEX_PLANES
-    if (ctx->node_tex) { cudaDestroyTextureObject(ctx->node_tex); ctx->node_tex = 0; }
-    if (node_count) {
-        cudaResourceDesc rd;
-        memset(&rd, 0, sizeof(rd));
-        rd.resType = cudaResourceTypeLinear;
-        rd.res.linear.devPtr = ctx->nodes.p;
-        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-        rd.res.linear.sizeInBytes = sizeof(BvhNode) * (n_bvh + 2);
-        cudaTextureDesc td;
-        memset(&td, 0, sizeof(td));
-        td.readMode = cudaReadModeElementType;
-        CU(cudaCreateTextureObject(&ctx->node_tex, &rd, &td, nullptr));
-    }
-    S.node_tex = ctx->node_tex;
-#endif
     cudaEventRecord(evb, st);
     CU(cudaStreamSynchronize(st));
     float ms0 = 0, ms1 = 0;
@@ -979,6 +965,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     }
     rt_stats& stats = ctx->stats;
     stats.rays_primary = stats.rays_shadow = stats.rays_secondary = stats.hits = stats.degenerate_rays = 0;
+    stats.shadow_rays_culled = 0;
     stats.ms_readback = 0;
     for (int k = 0; k < 2; k++) stats.nodes_fetched[k] = stats.tris_tested[k] = stats.spheres_tested[k] = 0;
     for (int k = 0; k < 4; k++) { stats.ms_kernel[k] = 0; stats.launches_kernel[k] = 0; }
@@ -1054,6 +1041,7 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
         stats.nodes_fetched[1] += c[CTR_S_NODES];
         stats.tris_tested[1] += c[CTR_S_TRIS];
         stats.spheres_tested[1] += c[CTR_S_SPHERES];
+        stats.shadow_rays_culled += c[CTR_S_CULLED];
     }
     stats.kernel_launches = J.launches;
     for (size_t k = 0; k + 1 < ctx->evused; k += 2) {
@@ -1138,6 +1126,14 @@ int replicate_scene(rt_context* ctx, int n) {
     CU(cudaSetDevice(ctx->device));
     for (int k = 0; k < n - 1; k++) {
         rt_context* pc = ctx->peers[(size_t)k];
+        if (pc->device == ctx->device) {      // sub-context on the primary's own device: same arrays, no copy
+            pc->S = ctx->S;
+            pc->sort_grid = ctx->sort_grid;
+            pc->sort_ok = ctx->sort_ok;
+            pc->node_bytes = ctx->node_bytes; pc->face_bytes = ctx->face_bytes;
+            pc->have_scene = true;
+            continue;
+        }
         auto copy = [&](auto& dst, const auto& src, size_t count) -> int {
             using T = std::remove_pointer_t<decltype(src.p)>;
             CU(cudaSetDevice(pc->device));
@@ -1263,6 +1259,7 @@ int render_multi(rt_context* ctx, const rt_params* p, void* out, bool out_is_pri
         const rt_stats& o = all[(size_t)k]->stats;
         st.rays_primary += o.rays_primary; st.rays_shadow += o.rays_shadow; st.rays_secondary += o.rays_secondary;
         st.degenerate_rays += o.degenerate_rays; st.kernel_launches += o.kernel_launches; st.hits += o.hits;
+        st.shadow_rays_culled += o.shadow_rays_culled;
         for (int j = 0; j < 2; j++) {
             st.nodes_fetched[j] += o.nodes_fetched[j]; st.tris_tested[j] += o.tris_tested[j]; st.spheres_tested[j] += o.spheres_tested[j];
         }
@@ -1575,9 +1572,7 @@ int rt_microbench_gather(rt_context* ctx, uint64_t array_bytes, int loads_per_th
     CU(data.ensure((size_t)nrec * 2));
     CU(sink.ensure(1));
     CU(cudaMemsetAsync(data.p, 0, (size_t)nrec * 32, ctx->stream));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, ctx->device));
-    const int blocks = prop.multiProcessorCount * 16, threads = 256;
+    const int blocks = ctx->num_sms * 16, threads = 256;
     k_gather_probe<<<blocks, threads, 0, ctx->stream>>>(data.p, nrec, loads_per_thread, sink.p);   // warm-up
     LAUNCHED("k_gather_probe", ctx->stream);
     float best = 1e30f;

@@ -160,9 +160,6 @@ struct DScene {
     // inside it.  A ray starting further out (only possible through rt_cast_rays) takes the
     // brute-force path instead.
     float origin_limit;
-    // the node array again, as a linear float4 texture (experiment RT_TEX_PLANES: plane loads through the TEX data
-    // pipe, which is separate from the LSU data pipe that limits the traversal kernels)
-    cudaTextureObject_t node_tex;
 };
 
 // ---- hit bookkeeping ------------------------------------------------------------
@@ -186,26 +183,54 @@ struct WorkCounters {
     unsigned long long nodes, tris, spheres;
 };
 
+// hitsBoundingBox (src/geometry.cpp:5-29): true when ANY of the six planes is crossed at t >= 0 inside the other two
+// coordinate ranges.  The reference tries the planes in a fixed order and returns at the first that passes; the
+// verdict is the OR over the planes, so the order is free.  A ray that starts inside the box (every shadow and
+// bounce ray of a mesh scene) passes at its EXIT plane, which an FP32 estimate picks first: one exact FP64 plane
+// test (the reference's own expressions) instead of 3.5 on average.  Only if that plane fails are all six
+// evaluated in the reference's order.
+__device__ __forceinline__ bool bbox_plane(const double* oo, const double* dd, int axis, int bn, const double* __restrict__ bbmin,
+                                           const double* __restrict__ bbmax) {
+    const double mag = dd[axis];
+    if (mag == 0.0) return false;
+    const double t = ((bn ? bbmax[axis] : bbmin[axis]) - oo[axis]) / mag;
+    if (t < 0) return false;
+    bool ok = true;
+#pragma unroll
+    for (int a2 = 0; a2 < 3; a2++) {
+        if (a2 == axis) continue;
+        const double ip = oo[a2] + t * dd[a2];
+        if (ip < bbmin[a2] || ip > bbmax[a2]) ok = false;
+    }
+    return ok;
+}
 __device__ __forceinline__ bool mesh_bbox(d3 o, d3 d, const double* __restrict__ bbmin,
                                           const double* __restrict__ bbmax) {
     const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    {   // likely exit plane: per axis the plane ahead of the ray, the nearest of the three (FP32 estimate)
+        float best = 3.0e38f;
+        int baxis = 0, bbn = 0;
+#pragma unroll
+        for (int axis = 0; axis < 3; axis++) {
+            const float df = (float)dd[axis];
+            if (df == 0.f) continue;
+            const int bn = df > 0.f ? 1 : 0;
+            const float tf = ((float)(bn ? bbmax[axis] : bbmin[axis]) - (float)oo[axis]) / df;
+            if (tf >= 0.f && tf < best) { best = tf; baxis = axis; bbn = bn; }
+        }
+        if (best < 3.0e38f) {
+            bool hit;
+            if (baxis == 0) hit = bbox_plane(oo, dd, 0, bbn, bbmin, bbmax);
+            else if (baxis == 1) hit = bbox_plane(oo, dd, 1, bbn, bbmin, bbmax);
+            else hit = bbox_plane(oo, dd, 2, bbn, bbmin, bbmax);
+            if (hit) return true;
+        }
+    }
 #pragma unroll
     for (int axis = 0; axis < 3; axis++) {
 #pragma unroll
-        for (int bn = 0; bn < 2; bn++) {
-            double mag = dd[axis];
-            if (mag == 0.0) continue;
-            double t = ((bn ? bbmax[axis] : bbmin[axis]) - oo[axis]) / mag;
-            if (t < 0) continue;
-            bool ok = true;
-#pragma unroll
-            for (int a2 = 0; a2 < 3; a2++) {
-                if (a2 == axis) continue;
-                double ip = oo[a2] + t * dd[a2];
-                if (ip < bbmin[a2] || ip > bbmax[a2]) ok = false;
-            }
-            if (ok) return true;
-        }
+        for (int bn = 0; bn < 2; bn++)
+            if (bbox_plane(oo, dd, axis, bn, bbmin, bbmax)) return true;
     }
     return false;
 }
@@ -395,9 +420,6 @@ __device__ __forceinline__ void slab1(const FRay& r, float nx, float ny, float n
     hit = tn <= tf;
 }
 
-#ifndef RT_TEX_PLANES
-#define RT_TEX_PLANES 0
-#endif
 #define RT_STACK 96
 #ifndef RT_ANYHIT_UNSORTED
 #define RT_ANYHIT_UNSORTED 1
@@ -511,18 +533,8 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
         const float4* pnx = reinterpret_cast<const float4*>(nb + (off + fr.nx));
         const float4* pny = reinterpret_cast<const float4*>(nb + (off + fr.ny));
         const float4* pnz = reinterpret_cast<const float4*>(nb + (off + fr.nz));
-#if RT_TEX_PLANES == 2
-        const float4 nx = tex1Dfetch<float4>(S.node_tex, (int)((off + fr.nx) >> 4)), ny = tex1Dfetch<float4>(S.node_tex, (int)((off + fr.ny) >> 4)),
-                     nz = tex1Dfetch<float4>(S.node_tex, (int)((off + fr.nz) >> 4));
-#else
         const float4 nx = __ldg(pnx), ny = __ldg(pny), nz = __ldg(pnz);
-#endif
-#if RT_TEX_PLANES >= 1
-        const float4 fx = tex1Dfetch<float4>(S.node_tex, (int)(((off + fr.nx) ^ 64u) >> 4)), fy = tex1Dfetch<float4>(S.node_tex, (int)(((off + fr.ny) ^ 64u) >> 4)),
-                     fz = tex1Dfetch<float4>(S.node_tex, (int)(((off + fr.nz) ^ 64u) >> 4));
-#else
         const float4 fx = __ldg(flip64(pnx)), fy = __ldg(flip64(pny)), fz = __ldg(flip64(pnz));
-#endif
         const int4 ref = __ldg(reinterpret_cast<const int4*>(nb + off + 48));
         if (COUNT) wc.nodes += 4;
         float t0, t1, t2, t3;

@@ -60,7 +60,8 @@ enum {
     CTR_NODES = 3, CTR_TRIS = 4, CTR_SPHERES = 5,          // closest-hit kernel
     CTR_S_NODES = 6, CTR_S_TRIS = 7, CTR_S_SPHERES = 8,    // shadow kernel
     CTR_NEXT_T = 9,                                        // refracted children (stored from the END of the next queue)
-    CTR_COUNT = 10
+    CTR_S_CULLED = 10,                                     // shadow rays answered without a traversal (COUNT builds)
+    CTR_COUNT = 12
 };
 
 struct FrameInfo {
@@ -399,31 +400,41 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADOW_MINBLOCKS) k_shadow(DScene
             const double INF = __longlong_as_double(0x7ff0000000000000ll);
             double dL = point ? norm4(toL) : INF;             // src/scene.cpp:89
             int inside = (h.meta[j] >> RT_META_INSIDE_SHIFT) & 1;
-            Best best;
-            bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc, stack_base<true>(sm_stack));
-            if (!occluded) {
-                const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
-                d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
-                double att[3];
-                if (point) {
-                    // src/lights.h:23-25.  pow(x, +-0) is exactly 1 for every x (IEEE 754 / C Annex F)
-                    const double fo = l->falloff;
-                    double f = fo == 0.0 ? 1.0 : (fo == 1.0 ? 1.0 / dL : (fo == 2.0 ? 1.0 / (dL * dL) : pow(dL, -fo)));
-                    for (int k = 0; k < 3; k++) att[k] = f * l->color[k];
-                } else {
-                    for (int k = 0; k < 3; k++) att[k] = l->color[k];
-                }
-                double di = ndl < 0.0 ? 0.0 : ndl;            // std::max(N.L, 0.0)
-                d3 R = (2 * ndl) * N - L;                     // src/scene.cpp:101-102
-                double mvr = -dot4(V, R);
-                // std::pow(std::max(-V.R, 0.0), sp); pow(+0, y > 0) is exactly +0 (C Annex F)
-                const double sp_ = m->sp;
-                double si = (mvr < 0.0 && sp_ > 0.0) ? 0.0 : pow_shading(mvr < 0.0 ? 0.0 : mvr, sp_);
-                int pixel = h.pixel[j];
-                for (int k = 0; k < 3; k++) {
-                    double w = h.fld(9 + k, j);
-                    double c = w * (di * att[k] * m->kd[k]) + w * (si * att[k] * m->ks[k]);
-                    atomicAdd(fb + (size_t)pixel * 3 + k, c);
+            // The Phong terms of this light (src/scene.cpp:95-106) BEFORE the occlusion query: when both are exactly
+            // zero (light behind the surface and no specular lobe towards the viewer) the light adds +0 whether or not
+            // it is occluded, so the query's answer cannot reach the frame and the traversal is skipped.  The
+            // reference casts that shadow ray too; it is still counted (rays_shadow = hits x lights on the host).
+            const DMat* m = S.mats + S.geoms[h.geom[j]].mat;
+            d3 V = mk3(h.fld(6, j), h.fld(7, j), h.fld(8, j));
+            double att[3];
+            if (point) {
+                // src/lights.h:23-25.  pow(x, +-0) is exactly 1 for every x (IEEE 754 / C Annex F)
+                const double fo = l->falloff;
+                double f = fo == 0.0 ? 1.0 : (fo == 1.0 ? 1.0 / dL : (fo == 2.0 ? 1.0 / (dL * dL) : pow(dL, -fo)));
+                for (int k = 0; k < 3; k++) att[k] = f * l->color[k];
+            } else {
+                for (int k = 0; k < 3; k++) att[k] = l->color[k];
+            }
+            double di = ndl < 0.0 ? 0.0 : ndl;                // std::max(N.L, 0.0)
+            d3 R = (2 * ndl) * N - L;                         // src/scene.cpp:101-102
+            double mvr = -dot4(V, R);
+            // std::pow(std::max(-V.R, 0.0), sp); pow(+0, y > 0) is exactly +0 (C Annex F)
+            const double sp_ = m->sp;
+            double si = (mvr < 0.0 && sp_ > 0.0) ? 0.0 : pow_shading(mvr < 0.0 ? 0.0 : mvr, sp_);
+            double c[3];
+            bool any = false;
+            for (int k = 0; k < 3; k++) {
+                double w = h.fld(9 + k, j);
+                c[k] = w * (di * att[k] * m->kd[k]) + w * (si * att[k] * m->ks[k]);
+                any = any || !(c[k] == 0.0);                  // NaN counts as a contribution (the reference would add it)
+            }
+            if (COUNT && !any) atomicAdd(ctr + CTR_S_CULLED, 1ull);
+            if (any) {
+                Best best;
+                bool occluded = cast_ray<true, BRUTE, COUNT>(S, P, L, lrev != (inside != 0), dL, best, wc, stack_base<true>(sm_stack));
+                if (!occluded) {
+                    int pixel = h.pixel[j];
+                    for (int k = 0; k < 3; k++) atomicAdd(fb + (size_t)pixel * 3 + k, c[k]);
                 }
             }
         }

@@ -185,6 +185,9 @@ typedef struct rt_stats {
     double   ms_trace;         /* device time of the last render (CUDA events) */
     double   ms_readback;      /* D2H of the result (host-buffer entry points) */
     uint64_t scene_bytes_h2d;  /* bytes copied host->device by the last rt_scene_upload */
+    uint64_t shadow_rays_culled; /* RT_FLAG_COUNT_WORK: shadow rays (counted in rays_shadow) whose light term is exactly
+                                    zero whether or not the light is occluded (src/scene.cpp:95-106: N.L <= 0 and no
+                                    specular lobe), answered without traversing the LBVH                            */
 } rt_stats;
 
 typedef struct rt_context rt_context;

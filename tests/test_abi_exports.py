@@ -65,3 +65,42 @@ def test_product_does_not_reference_the_oracle():
     for so in (pkg_dir / "lib").glob("*.so"):
         out = subprocess.run(["ldd", str(so)], capture_output=True, text=True).stdout
         assert "oracle" not in out and "libref" not in out
+
+
+def test_sub_rank_tiles_refine_a_ranks_share(pkg):
+    """rt_params.n_gpus inside a rank of a multi-process job: device k of n takes the tiles
+    (tx + ty) % (world * n) == rank + k * world, which must partition exactly the rank's own share."""
+    for (w, h) in [(33, 31), (1920, 1080), (7680, 4320), (500, 777)]:
+        for world in (1, 2, 3, 8):
+            for n in (2, 3, 4):
+                for rank in range(world):
+                    own = pkg.tile_counts(pkg.make_params(w, h, 5, tile_rank=rank, tile_world=world))[0]
+                    parts = [pkg.tile_counts(pkg.make_params(w, h, 5, tile_rank=rank + k * world, tile_world=world * n))[0]
+                             for k in range(n)]
+                    assert sum(parts) == own
+
+
+def test_abi_struct_layout_matches_the_header(pkg):
+    """ctypes mirrors of rt_params / rt_scene against the C compiler's view of include/rt_b200.h."""
+    import subprocess
+    import tempfile
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "rt_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt_params), offsetof(rt_params, n_gpus), sizeof(rt_scene),
+           offsetof(rt_scene, flags), offsetof(rt_scene, face_normals), sizeof(rt_stats), sizeof(rt_geometry));
+    return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        (ROOT / "include").exists()
+        c = f"{d}/layout.c"
+        open(c, "w").write(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), c, "-o", f"{d}/layout"], check=True)
+        out = subprocess.run([f"{d}/layout"], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [C.sizeof(pkg.rt_params), pkg.rt_params.n_gpus.offset, C.sizeof(pkg.rt_scene), pkg.rt_scene.flags.offset,
+            pkg.rt_scene.face_normals.offset, C.sizeof(pkg.rt_stats), C.sizeof(pkg.binding.rt_geometry)]
+    assert got == want
