@@ -569,8 +569,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
             peak_hbm, peak_src = float(mp["hbm_gbs"]), "measured"
         except Exception:
             pass
-        traffic_all = load_traffic(wl_name)
-        lanes_all = traffic_all.get("active_lanes", {})
+        traffic_all = load_traffic(wl_name)      # {kernel: {"dram_bytes_per_frame", "launches_per_frame", "active_lanes"}} from ncu
         if node_bytes > 0:
             walk_c, _ = ren.microbench_node_walk(32, 64)
             walk_d, _ = ren.microbench_node_walk(1, 64)
@@ -582,7 +581,9 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
             visits = cs["nodes_fetched"][k] / 4.0              # wide-node visits (4 child boxes each)
             nrays = (cs["rays_primary"] + cs["rays_secondary"]) if k == 0 else cs["rays_shadow"]
             ach = visits / (ms_k * 1e-3) if ms_k > 0 else 0.0
-            tr = traffic_all.get(kname)
+            prof = traffic_all.get(kname)
+            prof = prof if isinstance(prof, dict) else {}
+            tr = prof.get("dram_bytes_per_frame") if world == 1 and not emulate else None      # captured on the full single-GPU frame
             per_kernel[kname] = {
                 "ms_serial_frame": ms_k, "rays": int(nrays), "node_visits": visits, "visits_per_ray": visits / max(nrays, 1),
                 "exact_tests_per_ray": (cs["tris_tested"][k] + cs["spheres_tested"][k]) / max(nrays, 1),
@@ -590,7 +591,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
                 "frac_of_coherent_walk": ach / walk_c if walk_c else None,
                 "frac_of_divergent_walk": ach / walk_d if walk_d else None,
                 "lsu_bytes_gbs": ach * 112 / 1e9,
-                "active_lanes_per_instruction_ncu": lanes_all.get(kname),
+                "active_lanes_per_instruction_ncu": prof.get("active_lanes"),
                 "dram_bytes_per_frame_ncu": tr,
                 "dram_gbs": (tr / (ms_k * 1e-3) / 1e9) if (tr and ms_k > 0) else None,
                 "dram_frac_of_hbm_peak": (tr / (ms_k * 1e-3) / 1e9 / peak_hbm) if (tr and ms_k > 0) else None}
@@ -605,7 +606,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
             "achieved": dk["achieved_gvisits_s"], "peak": (walk_c / 1e9) if walk_c else None, "unit": "G wide-node visits/s",
             "frac": dk["frac_of_coherent_walk"], "peak_source": "measured in this run: rt_microbench_node_walk(group=32) on the scene's LBVH",
             "traffic": (dk["dram_bytes_per_frame_ncu"] / n_launch) if dk["dram_bytes_per_frame_ncu"] else None,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full, profiles/traffic.json)",
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel's launches of one frame / launches (ncu --set full of the single-GPU frame, profiles/traffic.json)",
             "launches_per_step": n_launch, "ms_per_launch": dk["ms_serial_frame"] / n_launch,
             "hbm_peak_gbs": peak_hbm, "hbm_peak_source": peak_src,
             "node_walk_gvisits_s": {"coherent_warp": (walk_c / 1e9) if walk_c else None, "divergent_lanes": (walk_d / 1e9) if walk_d else None},

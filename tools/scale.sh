@@ -1,5 +1,6 @@
-# 1/2/4/8-GPU scaling of the headline workload on one box (run under gpurun --gpus 8)
+# 1/2/4/8-GPU scaling of the headline workload on one box (run under gpurun --gpus 8); per_config rides along
+T=${1:-r02}
 for n in 8 4 2; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/${T}_scale_n$n.json 2> gpurun_out/${T}_scale_n$n.err
 done
-python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
+python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/${T}_scale_n1.json 2> gpurun_out/${T}_scale_n1.err
