@@ -62,9 +62,6 @@ static bool debug_sync() {
         if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "kernel %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
-#ifndef RT_TRACE_BUDGET_DEFAULT
-#define RT_TRACE_BUDGET_DEFAULT 0
-#endif
 #define RT_MAX_DEPTH 65535     // bounce_depth limit (check_params); counter blocks are allocated per level actually needed
 
 template <typename T>
@@ -152,10 +149,6 @@ struct rt_context {
     DevBuf<int> hi[2];                      // 3*(cap/2) each
     DevBuf<double> hsf;                     // unsorted hit records of the level being traced (hit sorting)
     DevBuf<int> hsi;
-    DevBuf<int> cont_i[2];                  // continuation records of suspended rays (k_trace_budget), ping-pong
-    DevBuf<double> cont_f[2];
-    DevBuf<unsigned long long> cont_s[2];
-    unsigned cont_cap = 0;
     DevBuf<uint32_t> skeys[2];              // radix-sort ping-pong buffers
     DevBuf<int> svals[2];
     DevBuf<int> shist;
@@ -651,9 +644,6 @@ struct RenderJob {
     unsigned long long* maxbits;   // intersection-only
     uint64_t launches;
     int max_level;                 // deepest bounce level that held rays
-    int budget[2];                 // node-visit budgets of the first and second k_trace_budget pass (0: plain k_trace)
-    size_t budget_min_rays;
-    int budget_first_level;
     // progress reporting (Scene::ProgressHandler, src/scene.cpp:41-47: every 100 ms on the calling thread)
     rt_progress_fn cb;
     void* cb_user;
@@ -739,47 +729,6 @@ int launch_trace(RenderJob& J, RayQ q, size_t off, int n, size_t nfront, HitQ h,
     LAUNCHED("k_trace", J.st);
     return RT_OK;
 }
-ContQ cont_queue(rt_context* ctx, int k) {
-    ContQ c;
-    const size_t cap = ctx->cont_cap;
-    c.ray = ctx->cont_i[k].p; c.cur = c.ray + cap; c.depth = c.cur + cap; c.geom = c.depth + cap; c.face = c.geom + cap;
-    c.f = ctx->cont_f[k].p;
-    c.stack = ctx->cont_s[k].p;
-    c.cap = (unsigned)cap;
-    return c;
-}
-
-// Closest hit with suspension of long rays (see ContQ): a budgeted first pass over the level's m rays, then passes
-// over the suspended ones, packed, until none is left (the third pass has no budget).
-template <bool COUNT>
-int launch_trace_budgeted(RenderJob& J, RayQ q, size_t off, int m, size_t nfront, HitQ h, unsigned long long* lc) {
-    rt_context* ctx = J.ctx;
-    unsigned long long* h_cont = ctx->h_ctr + 3;
-    int n = m;
-    for (int pass = 0;; pass++) {
-        CU(cudaMemsetAsync(lc + CTR_CONT, 0, sizeof(unsigned long long), J.st));
-        const int budget = pass < 2 ? J.budget[pass] : 0;
-        {
-            LaunchTimer lt(J, 0);
-            const unsigned blocks = (unsigned)((n + RT_BLOCK - 1) / RT_BLOCK);
-            if (pass == 0)
-                k_trace_budget<COUNT, false><<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, q, off, n, nfront, h, lc, cont_queue(ctx, 1),
-                                                                            cont_queue(ctx, 0), budget);
-            else
-                k_trace_budget<COUNT, true><<<blocks, RT_BLOCK, 0, J.st>>>(ctx->S, q, off, n, nfront, h, lc, cont_queue(ctx, (pass - 1) & 1),
-                                                                           cont_queue(ctx, pass & 1), budget);
-        }
-        J.launches++;
-        LAUNCHED("k_trace_budget", J.st);
-        if (budget <= 0) break;                  // an unbudgeted pass suspends nothing
-        CU(cudaMemcpyAsync(h_cont, lc + CTR_CONT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, J.st));
-        CU(cudaStreamSynchronize(J.st));
-        n = (int)std::min<unsigned long long>(*h_cont, ctx->cont_cap);
-        if (n == 0) break;
-    }
-    return RT_OK;
-}
-
 template <bool BRUTE, bool COUNT>
 int launch_shadow(RenderJob& J, int n, HitQ h, unsigned long long* lc, cudaStream_t st) {
     unsigned long long threads = (unsigned long long)n * (unsigned)J.ctx->S.num_slights;
@@ -835,10 +784,7 @@ int process_level(RenderJob& J, int level, int qi, size_t n, size_t nfront) {
             ht.geom = ctx->hsi.p + maxchunk;
             ht.meta = ctx->hsi.p + 2 * maxchunk;
         }
-        const bool budgeted = J.budget[0] > 0 && level >= J.budget_first_level && (size_t)m >= J.budget_min_rays && !J.brute && !ids_only &&
-                              ctx->S.nodes != nullptr && ctx->cont_cap > 0;
-        if (budgeted) lrc = J.count ? launch_trace_budgeted<true>(J, q, off, m, nfront, ht, lc) : launch_trace_budgeted<false>(J, q, off, m, nfront, ht, lc);
-        else if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, nfront, ht, lc) : launch_trace<true, false>(J, q, off, m, nfront, ht, lc);
+        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, nfront, ht, lc) : launch_trace<true, false>(J, q, off, m, nfront, ht, lc);
         else lrc = J.count ? launch_trace<false, true>(J, q, off, m, nfront, ht, lc) : launch_trace<false, false>(J, q, off, m, nfront, ht, lc);
         if (lrc != RT_OK) { release_q(); return lrc; }
         // everything enqueued on J.st from here on runs after this k_trace, the last reader of the queue
@@ -996,27 +942,6 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
             CU(ctx->svals[k].ensure(maxchunk));
         }
         CU(ctx->shist.ensure((size_t)256 * (SORT_MAX_BLOCKS + 1)));
-    }
-    {   // Suspension of long closest-hit rays (k_trace_budget): RT_TRACE_BUDGET / RT_TRACE_BUDGET2 = node visits a ray
-        // may spend in the first / second pass (0 = plain k_trace), on bounce levels >= RT_TRACE_BUDGET_FIRST_LEVEL
-        // with at least RT_TRACE_BUDGET_MIN_RAYS rays.
-        const char *b1 = getenv("RT_TRACE_BUDGET"), *b2 = getenv("RT_TRACE_BUDGET2"), *mr = getenv("RT_TRACE_BUDGET_MIN_RAYS"),
-                   *fl = getenv("RT_TRACE_BUDGET_FIRST_LEVEL");
-        J.budget[0] = b1 ? atoi(b1) : RT_TRACE_BUDGET_DEFAULT;
-        J.budget[1] = b2 ? atoi(b2) : 3 * J.budget[0];
-        J.budget_min_rays = mr ? (size_t)atoll(mr) : 262144;
-        J.budget_first_level = fl ? atoi(fl) : 1;
-        if (J.budget[0] > 0 && ctx->S.nodes && !ids_only && !p->intersection_only && !(p->flags & RT_FLAG_BRUTE_FORCE) && p->bounce_depth >= 1) {
-            const size_t ccap = std::max<size_t>(maxchunk / 4, 1024);
-            for (int k = 0; k < 2; k++) {
-                CU(ctx->cont_i[k].ensure(5 * ccap));
-                CU(ctx->cont_f[k].ensure(8 * ccap));
-                CU(ctx->cont_s[k].ensure((size_t)RT_CONT_STACK * ccap));
-            }
-            ctx->cont_cap = (unsigned)ccap;
-        } else {
-            ctx->cont_cap = 0;
-        }
     }
     ctx->hq_pending[0] = ctx->hq_pending[1] = false;
     ctx->evused = 0;

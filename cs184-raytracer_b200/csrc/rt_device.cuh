@@ -497,21 +497,6 @@ struct Stack {
         }
         top += RT_SH_STRIDE(ANYHIT);
     }
-    // number of entries / entry k counted from the bottom (suspending a traversal: see ContQ in rt_kernels.cuh)
-    __device__ __forceinline__ int size() const { return (int)((top - base) / RT_SH_STRIDE(ANYHIT)); }
-    __device__ __forceinline__ void entry(int k, int& ref, float& t) const {
-        const unsigned a = base + (unsigned)k * RT_SH_STRIDE(ANYHIT);
-        if (a < lim()) {
-            int tb = 0;
-            if (ANYHIT) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ref) : "r"(a));
-            else asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(a));
-            t = __int_as_float(tb);
-        } else {
-            const unsigned j = (a - lim()) / RT_SH_STRIDE(ANYHIT);
-            ref = sp.ref[j];
-            t = ANYHIT ? 0.f : sp.t[ANYHIT ? 0 : j];
-        }
-    }
     // Pops the next deferred subtree; closest hit: skips those a closer hit has made obsolete.
     __device__ __forceinline__ int pop(float tlim) {
         while (top != base) {
@@ -539,16 +524,10 @@ __device__ __forceinline__ const float4* flip64(const float4* p) {
 // Leaves are deferred through the same stack as internal nodes ("while-while"): this loop
 // only does cheap FP32 slab tests, so the threads of a warp reconverge before the long exact
 // FP64 primitive test instead of diverging into it.
-// BUDGETED: every node visit costs one unit of `budget`; when it is used up the loop returns with cur >= 0 (the
-// node that would have been visited next) and the caller suspends the ray.
-template <bool ANYHIT, bool COUNT, bool BUDGETED = false>
+template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float tlim, int& cur, Stack<ANYHIT>& st,
-                                        WorkCounters& wc, int* budget = nullptr) {
+                                        WorkCounters& wc) {
     while (cur >= 0) {
-        if (BUDGETED) {
-            if (*budget <= 0) return;
-            (*budget)--;
-        }
         const char* const nb = reinterpret_cast<const char*>(S.nodes);
         const unsigned off = (unsigned)cur * (unsigned)sizeof(BvhNode);       // node arrays stay below 4 GB: rt_scene_upload rejects more than 2^25 nodes
         const float4* pnx = reinterpret_cast<const float4*>(nb + (off + fr.nx));
@@ -605,25 +584,6 @@ __device__ __forceinline__ void descend(const DScene& S, const FRay& fr, float t
         } else {
             cur = st.pop(tlim);
         }
-    }
-}
-
-// The LBVH part of a closest-hit query as a loop that can be SUSPENDED: with BUDGETED it returns false once
-// `budget` node visits are used up, leaving the ray's whole traversal state in (cur, st, best, R is a cache and
-// may be dropped); called again with that state it goes on exactly where it stopped, so the result is the one of
-// an uninterrupted traversal.  Returns true when the traversal is complete.
-template <bool COUNT, bool BUDGETED>
-__device__ __forceinline__ bool closest_loop(const DScene& S, d3 o, d3 d, bool reverse, const FRay& fr, Best& best, ObjRay& R,
-                                             Stack<false>& st, int& cur, WorkCounters& wc, int budget) {
-    float tlim = best.geom >= 0 ? prune_limit(best.wd) : __int_as_float(0x7f800000);
-    while (true) {
-        descend<false, COUNT, BUDGETED>(S, fr, tlim, cur, st, wc, &budget);
-        if (cur == BVH_DONE) return true;
-        if (BUDGETED && cur >= 0) return false;               // budget used up in front of node `cur`
-        test_prim<false, COUNT>(S, ~cur, o, d, reverse, 0.0, R, best, wc);
-        if (best.geom >= 0) tlim = prune_limit(best.wd);
-        cur = st.pop(tlim);
-        if (cur == BVH_DONE) return true;
     }
 }
 

@@ -61,7 +61,6 @@ enum {
     CTR_S_NODES = 6, CTR_S_TRIS = 7, CTR_S_SPHERES = 8,    // shadow kernel
     CTR_NEXT_T = 9,                                        // refracted children (stored from the END of the next queue)
     CTR_S_CULLED = 10,                                     // shadow rays answered without a traversal (COUNT builds)
-    CTR_CONT = 11,                                         // rays suspended by the current k_trace_budget pass
     CTR_COUNT = 12
 };
 
@@ -175,118 +174,6 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S
     }
     bool hit = active && best.geom >= 0;
     unsigned slot = warp_append(hit, ctr + CTR_HITS);
-    if (hit) {
-        h.fld(0, slot) = best.P.x; h.fld(1, slot) = best.P.y; h.fld(2, slot) = best.P.z;
-        h.fld(3, slot) = best.N.x; h.fld(4, slot) = best.N.y; h.fld(5, slot) = best.N.z;
-        h.fld(6, slot) = d.x; h.fld(7, slot) = d.y; h.fld(8, slot) = d.z;
-        h.fld(9, slot) = q.fld(6, i); h.fld(10, slot) = q.fld(7, i); h.fld(11, slot) = q.fld(8, i);
-        h.fld(12, slot) = best.wd;
-        h.pixel[slot] = pixel;
-        h.geom[slot] = best.geom;
-        h.meta[slot] = meta;
-    }
-    flush_work<COUNT>(wc, ctr + CTR_NODES);
-}
-
-// ---- long rays: suspend and continue in a compacted launch --------------------------------------------------
-// On the bounce levels a warp of k_trace lives as long as its longest ray while most of its lanes have retired
-// (ncu, round 1/2: 12 of 32 lanes active per instruction; the mean is 19 node visits, the tail several times
-// that).  k_trace_budget gives every ray a budget of node visits.  A ray that uses it up is SUSPENDED: its whole
-// traversal state — the node it was about to visit, the deferred-subtree stack, the closest hit so far — goes
-// into a continuation record, and the next pass runs only those rays, packed into full warps, with a larger
-// budget (the last pass has none).  The traversal of a ray is the same sequence of steps whether or not it was
-// interrupted, so hits, ids and ray counts do not change.
-#define RT_CONT_STACK 24                 // saved stack entries per record; a deeper stack restarts from the root
-struct ContQ {
-    int* ray;                  // number g of the ray within its level (see k_trace): o, d, weight, meta are re-read
-    int* cur;                  // node in front of which the budget ran out
-    int* depth;                // saved stack entries, -1: restart from the root (the closest hit so far still prunes)
-    int* geom;                 // closest hit so far: geometry (-1 none), face
-    int* face;
-    double* f;                 // 8 fields SoA: dobj wd P(3) N(3)
-    unsigned long long* stack; // RT_CONT_STACK x cap entries SoA: (t bits << 32) | ref
-    unsigned cap;              // slots; 0 = no suspension (plain closest hit)
-    __device__ __forceinline__ double& fld(int k, size_t i) const { return f[(size_t)k * cap + i]; }
-};
-
-template <bool COUNT, bool RESUME>
-__global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace_budget(DScene S, RayQ q, size_t off, int n, size_t nfront, HitQ h,
-                                                            unsigned long long* ctr, ContQ in, ContQ out, int budget) {
-    __shared__ __align__(16) unsigned char sm_stack[RT_SH_STACK_BYTES(false)];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = t < n;
-    size_t g = 0;
-    if (active) g = RESUME ? (size_t)(unsigned)in.ray[t] : off + (size_t)t;
-    const size_t i = g < nfront ? g : q.cap - 1 - (g - nfront);
-    int pixel = active ? q.pixel[i] : -1;
-    active = active && pixel >= 0;
-    Best best;
-    best.geom = -1; best.face = -1; best.dobj = 0.0; best.wd = 0.0;
-    WorkCounters wc = {0, 0, 0};
-    d3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
-    int meta = 0, cur = BVH_DONE;
-    bool reverse = false;
-    StackSpill<false> spill;
-    Stack<false> st(stack_base<false>(sm_stack), spill);
-    ObjRay R;
-    R.geom = -1; R.box_ok = 1;
-    FRay fr;
-    if (active) {
-        o = mk3(q.fld(0, i), q.fld(1, i), q.fld(2, i));
-        d = mk3(q.fld(3, i), q.fld(4, i), q.fld(5, i));
-        meta = q.meta[i];
-        reverse = (meta >> RT_META_INSIDE_SHIFT) & 1;
-        fr = make_fray(o, d);
-        if (!RESUME) {
-            // the primitives outside the LBVH first, like cast_ray
-            for (int k = 0; k < S.num_flat; k++) test_prim<false, COUNT>(S, __ldg(S.flat + k), o, d, reverse, 0.0, R, best, wc);
-            cur = 0;
-        } else {
-            best.geom = in.geom[t]; best.face = in.face[t];
-            best.dobj = in.fld(0, t); best.wd = in.fld(1, t);
-            best.P = mk3(in.fld(2, t), in.fld(3, t), in.fld(4, t));
-            best.N = mk3(in.fld(5, t), in.fld(6, t), in.fld(7, t));
-            const int depth = in.depth[t];
-            cur = depth < 0 ? 0 : in.cur[t];
-            for (int k = 0; k < depth; k++) {
-                const unsigned long long e = in.stack[(size_t)k * in.cap + t];
-                st.push((int)(unsigned)e, __int_as_float((int)(e >> 32)));
-            }
-        }
-    }
-    // Traverse; a ray whose budget runs out takes a slot of the next pass' queue and saves its state there.  Should
-    // that queue be full, the ray goes round the loop once more without a budget (a single instance of the
-    // traversal code serves both cases).
-    int b = budget > 0 ? budget : 0x7fffffff;
-    bool done = !active, susp = false;
-    while (true) {
-        const bool fin = done ? true : closest_loop<COUNT, true>(S, o, d, reverse, fr, best, R, st, cur, wc, b);
-        const bool want = !done && !fin;
-        const unsigned cslot = warp_append(want, ctr + CTR_CONT);
-        const bool overflow = want && cslot >= out.cap;
-        if (want && !overflow) {
-            const int depth = st.size();
-            out.ray[cslot] = (int)g;
-            out.cur[cslot] = cur;
-            out.depth[cslot] = depth <= RT_CONT_STACK ? depth : -1;
-            out.geom[cslot] = best.geom; out.face[cslot] = best.face;
-            out.fld(0, cslot) = best.dobj; out.fld(1, cslot) = best.wd;
-            out.fld(2, cslot) = best.P.x; out.fld(3, cslot) = best.P.y; out.fld(4, cslot) = best.P.z;
-            out.fld(5, cslot) = best.N.x; out.fld(6, cslot) = best.N.y; out.fld(7, cslot) = best.N.z;
-            if (depth <= RT_CONT_STACK)
-                for (int k = 0; k < depth; k++) {
-                    int ref; float te;
-                    st.entry(k, ref, te);
-                    out.stack[(size_t)k * out.cap + cslot] = ((unsigned long long)(unsigned)__float_as_int(te) << 32) | (unsigned)ref;
-                }
-            susp = true;
-        }
-        done = done || fin || (want && !overflow);
-        if (!__any_sync(0xffffffffu, overflow)) break;
-        b = 0x7fffffff;
-    }
-    const bool hit = active && !susp && best.geom >= 0;
-    const unsigned slot = warp_append(hit, ctr + CTR_HITS);
     if (hit) {
         h.fld(0, slot) = best.P.x; h.fld(1, slot) = best.P.y; h.fld(2, slot) = best.P.z;
         h.fld(3, slot) = best.N.x; h.fld(4, slot) = best.N.y; h.fld(5, slot) = best.N.z;
