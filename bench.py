@@ -301,7 +301,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
               "partition": f"interleaved 32x32 tiles over {world} rank(s), scene replicated",
               "assemble": "single rank: row-major RGB8 frame on the device" if world == 1 else
                           ("peer: every rank's resolve kernel stores its tiles into rank 0's frame (CUDA IPC mapping, NVLink), "
-                           "one 4-byte all-reduce per frame as the completion barrier" if args.assemble == "peer" else
+                           "one 4-byte all-reduce per frame as the completion barrier; two frames in flight (double-buffered)" if args.assemble == "peer" else
                            "nccl: dist.gather of the packed RGB8 tiles + unpack kernel on rank 0 (round-1 path, A/B)"),
               "l2": "no explicit flush: every frame streams its ray and hit queues (80 B / 116 B per record, 10^6..10^8 records per bounce "
                     "level) through the 126 MB L2 between two uses of any scene data"}
@@ -329,7 +329,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
     own_tiles, max_tiles, total_tiles = pkg.tile_counts(p)
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
     shared_ptr = None
-    frame = gathered = packed_all = None
+    frame = gathered = packed_all = frames2 = None
     if world == 1 and emulate:
         out = torch.zeros(nbytes if sub > 1 else max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
         out_ptr = out.data_ptr()
@@ -337,17 +337,22 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
         frame = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out_ptr = frame.data_ptr()
     elif peer:
-        handle = [None]
+        # two shared frames (double buffering): frame k goes into buffer k & 1 and its completion barrier is only
+        # waited for before frame k + 2 overwrites that buffer, so a rank may run one frame ahead of the slowest
+        handle = [None, None]
+        shared_ptr = [None, None]
         if rank == 0:
-            shared_ptr, h = ren.shared_frame_create(nbytes)
-            handle = [h]
+            for b in range(2):
+                shared_ptr[b], handle[b] = ren.shared_frame_create(nbytes)
         dist.broadcast_object_list(handle, src=0)
         if rank != 0:
-            shared_ptr = ren.shared_frame_open(handle[0])
-        out_ptr = shared_ptr
+            shared_ptr = [ren.shared_frame_open(h) for h in handle]
+        out_ptr = shared_ptr[0]
         if rank == 0:
-            frame = torch.as_tensor(RawDevice(shared_ptr, nbytes), device=dev)
-            frame.zero_()
+            frames2 = [torch.as_tensor(RawDevice(ptr, nbytes), device=dev) for ptr in shared_ptr]
+            for f in frames2:
+                f.zero_()
+            frame = frames2[0]
     else:
         out = torch.zeros(max_tiles * pkg.RT_TILE_PIXELS * 3, dtype=torch.uint8, device=dev)
         out_ptr = out.data_ptr()
@@ -356,8 +361,12 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
         gathered = list(packed_all.chunk(world)) if rank == 0 else None
         frame = torch.empty(nbytes, dtype=torch.uint8, device=dev) if rank == 0 else None
 
+    ticks = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2)]
+    pending = [None, None]
+    counter = {"k": 0}
+
     def assemble(pp):
-        """What follows a rank's render until the frame is complete on rank 0."""
+        """What follows a rank's render until the frame is complete on rank 0 (round-1 path and the e2e fallback)."""
         if world == 1:
             return
         if peer:
@@ -367,9 +376,23 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
             if rank == 0:
                 ren.unpack_tiles(pp, packed_all.data_ptr(), frame.data_ptr(), rgb8=True, stream=stream)
 
+    def drain():
+        for b in range(2):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
+
     def step():
-        ren.render_device(p, out_ptr, rgb8=True, stream=stream)
-        assemble(p)
+        if not peer:
+            ren.render_device(p, out_ptr, rgb8=True, stream=stream)
+            assemble(p)
+            return
+        b = counter["k"] & 1
+        counter["k"] += 1
+        if pending[b] is not None:
+            pending[b].wait()                   # frame k - 2 is complete on every rank: its buffer may be overwritten
+        ren.render_device(p, shared_ptr[b], rgb8=True, stream=stream)     # returns when this rank's tiles are stored
+        pending[b] = dist.all_reduce(ticks[b], async_op=True)              # 4-byte completion barrier of frame k
 
     def sync_all():
         torch.cuda.synchronize()
@@ -379,6 +402,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
 
     for _ in range(max(warmup, 0)):
         step()
+    drain()
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -391,8 +415,11 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
         st = ren.stats()
         agg["ms_kernel"] += np.array(st["ms_kernel"]); agg["launches_kernel"] += np.array(st["launches_kernel"])
         agg["launches"] += st["kernel_launches"] + (1 if (world > 1 and rank == 0 and not peer) else 0)
+    drain()                                     # the last frames' barriers belong to the timed region
     e1.record()
     sync_all()
+    if peer and rank == 0:
+        frame = frames2[(counter["k"] - 1) & 1]      # the frame rendered last
     clocks = sampler.stop() if rank == 0 else None
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     rays = torch.tensor([st["rays_primary"], st["rays_shadow"], st["rays_secondary"], agg["launches"]], dtype=torch.float64, device=dev)
@@ -499,7 +526,7 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
                 ren.render_device(p, out_ptr, rgb8=True, stream=stream)
                 assemble(p)
                 if rank == 0:
-                    torch.from_numpy(host_np).copy_(frame)
+                    torch.from_numpy(host_np).copy_(frames2[0] if peer else frame)
             torch.cuda.synchronize()
 
         e2e_step()
@@ -638,14 +665,16 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
             cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
     if peer and shared_ptr is not None:
-        frame = None
+        frame = frames2 = None
         torch.cuda.synchronize()
         dist.barrier()
         if rank != 0:
-            ren.shared_frame_close(shared_ptr)
+            for ptr in shared_ptr:
+                ren.shared_frame_close(ptr)
         dist.barrier()
         if rank == 0:
-            ren.shared_frame_close(shared_ptr)
+            for ptr in shared_ptr:
+                ren.shared_frame_close(ptr)
     ren.close()
     host_scene.close()
     if rank != 0:
