@@ -326,6 +326,11 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
         p.n_gpus = sub
         p.flags |= pkg.RT_FLAG_FULL_FRAME
         config["partition"] += f"; {sub} concurrent sub-contexts per GPU"
+    if args.in_process > 1 and world == 1:
+        # ONE process drives N GPUs through rt_params.n_gpus (what `as2 --gpus N` does): worker thread per device inside
+        # the library, scene replicated with peer copies, every device's resolve kernel stores into this frame over NVLink
+        p.n_gpus = args.in_process
+        config["partition"] = f"interleaved 32x32 tiles over {args.in_process} GPUs of ONE process (rt_params.n_gpus), scene replicated by peer copies"
     own_tiles, max_tiles, total_tiles = pkg.tile_counts(p)
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
     shared_ptr = None
@@ -488,7 +493,8 @@ def run_workload(args, pkg, torch, dist, wl_name, headline):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             host_shared = bool(ok.item())
         pe = pkg.make_params(width, height, depth, tile_rank=rank, tile_world=world,
-                             flags=pkg.RT_FLAG_FULL_FRAME if world > 1 else 0)
+                             flags=pkg.RT_FLAG_FULL_FRAME if world > 1 else 0,
+                             n_gpus=args.in_process if (args.in_process > 1 and world == 1) else 0)
         split_upload = world > 1 and nf >= 4096
         if split_upload:
             per = (nf + world - 1) // world
@@ -697,6 +703,8 @@ def main():
                     help="N > 1: peer = resolve kernels store into rank 0's frame over NVLink (default); nccl = gather + unpack (A/B)")
     ap.add_argument("--configs", default="all", choices=["all", "none"],
                     help="all: after the headline workload also time the other BASELINE.json configs (per_config)")
+    ap.add_argument("--in-process", type=int, default=0,
+                    help="single process: render with rt_params.n_gpus = N (the library drives N GPUs itself); not the driver's launch mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -756,6 +764,7 @@ def main():
         line = {"metric": "Mrays/s (primary+shadow+secondary)", "value": head["value"], "unit": "Mrays/s", "n_gpus": world,
                 "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": head["config"],
+                "gpus_in_process": args.in_process if args.in_process > 1 else None,
                 "rays_per_step": head["rays_per_step"], "frame_ms": head["frame_ms"], "ms_scene_upload": head["ms_scene_upload"],
                 "ms_lbvh_build": head["ms_lbvh_build"], "clocks": head["clocks"], "e2e": head["e2e"],
                 "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"],
