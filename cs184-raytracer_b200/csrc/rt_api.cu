@@ -644,6 +644,7 @@ struct RenderJob {
     unsigned long long* maxbits;   // intersection-only
     uint64_t launches;
     int max_level;                 // deepest bounce level that held rays
+    PrimaryRays primary;           // bounce level 0 without a ray queue: k_trace generates the camera rays itself
     // progress reporting (Scene::ProgressHandler, src/scene.cpp:41-47: every 100 ms on the calling thread)
     rt_progress_fn cb;
     void* cb_user;
@@ -720,11 +721,11 @@ int acquire_queue(rt_context* ctx, int* out) {
 }
 void release_queue(rt_context* ctx, int qi) { ctx->qpool[(size_t)qi].busy = false; }
 
-template <bool BRUTE, bool COUNT>
+template <bool BRUTE, bool COUNT, bool PRIMARY = false>
 int launch_trace(RenderJob& J, RayQ q, size_t off, int n, size_t nfront, HitQ h, unsigned long long* lc) {
     LaunchTimer lt(J, 0);
-    k_trace<BRUTE, COUNT><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, nfront, h, lc,
-                                                                            J.ids_geom, J.ids_face);
+    k_trace<BRUTE, COUNT, PRIMARY><<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, J.st>>>(J.ctx->S, q, off, n, nfront, h, lc,
+                                                                                     J.ids_geom, J.ids_face, J.primary);
     J.launches++;
     LAUNCHED("k_trace", J.st);
     return RT_OK;
@@ -762,8 +763,11 @@ int process_level(RenderJob& J, int level, int qi, size_t n, size_t nfront) {
     // this level's counter block (CTR_HITS / CTR_NEXT are reset per chunk, the rest accumulate)
     unsigned long long* lc = ctx->ctr.p + (CTR_COUNT + 1) + (size_t)level * CTR_COUNT;
     unsigned long long* h_pair = ctx->h_ctr;
-    const RayQ q = pool_queue(ctx, qi);
-    bool q_released = false;
+    const bool fused_primary = qi < 0;          // level 0, rays generated inside k_trace
+    RayQ q;
+    memset(&q, 0, sizeof(q));
+    if (!fused_primary) q = pool_queue(ctx, qi);
+    bool q_released = fused_primary;
     auto release_q = [&]() { if (!q_released) { release_queue(ctx, qi); q_released = true; } };
     for (size_t off = 0; off < n; off += maxchunk) {
         const int m = (int)std::min(maxchunk, n - off);
@@ -784,7 +788,8 @@ int process_level(RenderJob& J, int level, int qi, size_t n, size_t nfront) {
             ht.geom = ctx->hsi.p + maxchunk;
             ht.meta = ctx->hsi.p + 2 * maxchunk;
         }
-        if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, nfront, ht, lc) : launch_trace<true, false>(J, q, off, m, nfront, ht, lc);
+        if (fused_primary) lrc = J.count ? launch_trace<false, true, true>(J, q, off, m, nfront, ht, lc) : launch_trace<false, false, true>(J, q, off, m, nfront, ht, lc);
+        else if (J.brute) lrc = J.count ? launch_trace<true, true>(J, q, off, m, nfront, ht, lc) : launch_trace<true, false>(J, q, off, m, nfront, ht, lc);
         else lrc = J.count ? launch_trace<false, true>(J, q, off, m, nfront, ht, lc) : launch_trace<false, false>(J, q, off, m, nfront, ht, lc);
         if (lrc != RT_OK) { release_q(); return lrc; }
         // everything enqueued on J.st from here on runs after this k_trace, the last reader of the queue
@@ -816,6 +821,9 @@ int process_level(RenderJob& J, int level, int qi, size_t n, size_t nfront) {
         const bool last_level = level >= J.p->bounce_depth;
         int nqi = -1;
         RayQ next = q;                          // unused by k_shade on the last level (depth 0: nothing is spawned)
+        if (last_level && fused_primary) {      // ... but it must be a valid queue descriptor all the same
+            next.cap = 1;
+        }
         if (!last_level) {
             int rc = acquire_queue(ctx, &nqi);
             if (rc != RT_OK) { release_q(); return rc; }
@@ -988,15 +996,18 @@ int render_core(rt_context* ctx, const rt_params* p, cudaStream_t st, bool ids_o
     for (long long first = 0; first < nslots; first += slots_per_batch) {
         const long long nslot_batch = std::min<long long>(slots_per_batch, nslots - first);
         const int n = (int)(nslot_batch * sub * sub);
-        int q0 = -1;
-        rc = acquire_queue(ctx, &q0);
-        if (rc != RT_OK) return rc;
-        {
-            LaunchTimer lt(J, 3);
-            k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, F, first, n, p->bounce_depth, pool_queue(ctx, q0), sub);
+        J.primary.F = F; J.primary.first_slot = first; J.primary.sub = sub; J.primary.depth = p->bounce_depth;
+        int q0 = -1;                   // stays -1 when k_trace generates the camera rays itself
+        if (J.brute) {
+            rc = acquire_queue(ctx, &q0);
+            if (rc != RT_OK) return rc;
+            {
+                LaunchTimer lt(J, 3);
+                k_raygen<<<(n + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(ctx->S, J.primary, n, pool_queue(ctx, q0));
+            }
+            J.launches++;
+            LAUNCHED("k_raygen", st);
         }
-        J.launches++;
-        LAUNCHED("k_raygen", st);
         // progress is counted in pixels of the WHOLE frame: this context's slots stand for tile_world times as many
         J.px_before_batch = std::min<long long>(first * (long long)p->tile_world, total_px - 1);
         J.px_batch = std::min<long long>(nslot_batch * (long long)p->tile_world, total_px - 1 - J.px_before_batch);

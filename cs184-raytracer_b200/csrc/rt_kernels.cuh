@@ -110,39 +110,54 @@ __device__ __forceinline__ void flush_work(const WorkCounters& wc, unsigned long
     }
 }
 
-// sub > 1: supersampling — queue entry i is sample (i % sub^2) of slot first_slot + i / sub^2; its ray goes
-// through the centre of cell (si, sj) of the sub x sub grid inside the pixel and carries weight 1/sub^2.
-__global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long long first_slot, int n, int depth,
-                                                      RayQ q, int sub) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int ss = sub * sub;
-    long long slot = first_slot + (sub > 1 ? i / ss : i);
+// Camera ray of queue entry i (Camera::calculateViewingRay, src/rtbase.h:74-84, from the pixel loop of
+// src/scene.cpp:26-30).  sub > 1: supersampling — entry i is sample (i % sub^2) of slot first_slot + i / sub^2; its ray
+// goes through the centre of cell (si, sj) of the sub x sub grid inside the pixel and carries weight 1/sub^2.
+// Returns the framebuffer slot, or -1 for a slot outside the frame / a degenerate ray (the Ray ctor would throw).
+struct PrimaryRays {
+    FrameInfo F;
+    long long first_slot;
+    int sub;
+    int depth;
+};
+__device__ __forceinline__ int primary_ray(const DScene& S, const PrimaryRays& pr, int i, d3& E, d3& d, double& w) {
+    const int ss = pr.sub * pr.sub;
+    const long long slot = pr.first_slot + (pr.sub > 1 ? i / ss : i);
     int px, py;
-    if (!slot_to_pixel(F, slot, px, py)) { q.pixel[i] = -1; return; }
-    double rowFrac = (py + 0.5) / F.height, colFrac = (px + 0.5) / F.width;
-    double w = 1.0;
-    if (sub > 1) {
-        const int k = i % ss, si = k % sub, sj = k / sub;
-        rowFrac = (py + (sj + 0.5) / sub) / F.height;
-        colFrac = (px + (si + 0.5) / sub) / F.width;
+    if (!slot_to_pixel(pr.F, slot, px, py)) return -1;
+    double rowFrac = (py + 0.5) / pr.F.height, colFrac = (px + 0.5) / pr.F.width;
+    w = 1.0;
+    if (pr.sub > 1) {
+        const int k = i % ss, si = k % pr.sub, sj = k / pr.sub;
+        rowFrac = (py + (sj + 0.5) / pr.sub) / pr.F.height;
+        colFrac = (px + (si + 0.5) / pr.sub) / pr.F.width;
         w = 1.0 / ss;
     }
     const DCamera& c = S.cam;
     d3 LR = mk3(c.lr[0], c.lr[1], c.lr[2]), UR = mk3(c.ur[0], c.ur[1], c.ur[2]);
     d3 LL = mk3(c.ll[0], c.ll[1], c.ll[2]), UL = mk3(c.ul[0], c.ul[1], c.ul[2]);
-    d3 E = mk3(c.eye[0], c.eye[1], c.eye[2]);
+    E = mk3(c.eye[0], c.eye[1], c.eye[2]);
     d3 right = rowFrac * LR + (1.0 - rowFrac) * UR;
     d3 left = rowFrac * LL + (1.0 - rowFrac) * UL;
     d3 ip = colFrac * right + (1.0 - colFrac) * left;
     d3 raw = ip - E;
-    bool ok = !(raw.x == 0 && raw.y == 0 && raw.z == 0);   // Ray ctor would throw (src/rtbase.h:19-20)
-    d3 d = ok ? ray_normalize(raw) : raw;
+    const bool ok = !(raw.x == 0 && raw.y == 0 && raw.z == 0);   // Ray ctor would throw (src/rtbase.h:19-20)
+    d = ok ? ray_normalize(raw) : raw;
+    return ok ? (int)slot : -1;
+}
+
+// Primary rays into a ray queue (only when the closest-hit kernel does not generate them itself: brute force).
+__global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, PrimaryRays pr, int n, RayQ q) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 E = mk3(0, 0, 0), d = mk3(0, 0, 1);
+    double w = 1.0;
+    const int slot = primary_ray(S, pr, i, E, d, w);
     q.fld(0, i) = E.x; q.fld(1, i) = E.y; q.fld(2, i) = E.z;
     q.fld(3, i) = d.x; q.fld(4, i) = d.y; q.fld(5, i) = d.z;
     q.fld(6, i) = w; q.fld(7, i) = w; q.fld(8, i) = w;
-    q.pixel[i] = ok ? (int)slot : -1;
-    q.meta[i] = depth;
+    q.pixel[i] = slot;
+    q.meta[i] = pr.depth;
 }
 
 // Closest hit for every queued ray; hits are appended (compacted) to the hit queue.
@@ -150,25 +165,35 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(DScene S, FrameInfo F, long
 // The queue holds its rays in two regions: entries [0, nfront) from the front (camera rays; reflected children) and
 // the rest from the END backwards (refracted children), so a warp is one class of rays from neighbouring origins
 // instead of an interleaving of the two.  Ray number g of the level sits at g (g < nfront) or cap - 1 - (g - nfront).
-template <bool BRUTE, bool COUNT>
+// PRIMARY: the rays of bounce level 0 are generated here (primary_ray) instead of being read from a queue a separate
+// kernel filled — 80 B written and 80 B read per primary ray that never need to exist.
+template <bool BRUTE, bool COUNT, bool PRIMARY>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S, RayQ q, size_t off, int n, size_t nfront, HitQ h,
-                                                     unsigned long long* ctr, int* ids_geom, int* ids_face) {
+                                                     unsigned long long* ctr, int* ids_geom, int* ids_face, PrimaryRays pr) {
     __shared__ __align__(16) unsigned char sm_stack[RT_SH_STACK_BYTES(false)];
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t g = off + (size_t)t;
-    const size_t i = g < nfront ? g : q.cap - 1 - (g - nfront);
+    const size_t i = PRIMARY ? 0 : (g < nfront ? g : q.cap - 1 - (g - nfront));
     bool active = t < n;
-    int pixel = active ? q.pixel[i] : -1;
-    active = active && pixel >= 0;
     Best best;
     best.geom = -1;
     WorkCounters wc = {0, 0, 0};
     d3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
-    int meta = 0;
+    double w0 = 1.0;
+    int meta = 0, pixel = -1;
+    if (PRIMARY) {
+        if (active) pixel = primary_ray(S, pr, t, o, d, w0);
+        meta = pr.depth;
+    } else {
+        pixel = active ? q.pixel[i] : -1;
+    }
+    active = active && pixel >= 0;
     if (active) {
-        o = mk3(q.fld(0, i), q.fld(1, i), q.fld(2, i));
-        d = mk3(q.fld(3, i), q.fld(4, i), q.fld(5, i));
-        meta = q.meta[i];
+        if (!PRIMARY) {
+            o = mk3(q.fld(0, i), q.fld(1, i), q.fld(2, i));
+            d = mk3(q.fld(3, i), q.fld(4, i), q.fld(5, i));
+            meta = q.meta[i];
+        }
         cast_ray<false, BRUTE, COUNT>(S, o, d, (meta >> RT_META_INSIDE_SHIFT) & 1, 0.0, best, wc, stack_base<false>(sm_stack));
         if (ids_geom) { ids_geom[pixel] = best.geom; ids_face[pixel] = best.face; }
     }
@@ -178,7 +203,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MINBLOCKS) k_trace(DScene S
         h.fld(0, slot) = best.P.x; h.fld(1, slot) = best.P.y; h.fld(2, slot) = best.P.z;
         h.fld(3, slot) = best.N.x; h.fld(4, slot) = best.N.y; h.fld(5, slot) = best.N.z;
         h.fld(6, slot) = d.x; h.fld(7, slot) = d.y; h.fld(8, slot) = d.z;
-        h.fld(9, slot) = q.fld(6, i); h.fld(10, slot) = q.fld(7, i); h.fld(11, slot) = q.fld(8, i);
+        if (PRIMARY) { h.fld(9, slot) = w0; h.fld(10, slot) = w0; h.fld(11, slot) = w0; }
+        else { h.fld(9, slot) = q.fld(6, i); h.fld(10, slot) = q.fld(7, i); h.fld(11, slot) = q.fld(8, i); }
         h.fld(12, slot) = best.wd;
         h.pixel[slot] = pixel;
         h.geom[slot] = best.geom;
