@@ -433,3 +433,80 @@ def test_pathb_reference_main_on_the_b200(tmp_path):
         gold = decode_png(GOLDEN / "outputs" / f"image-{n}.png")
         diff = np.abs(img.astype(np.int16) - gold.astype(np.int16)).max(axis=2)
         assert float((diff <= 1).mean()) >= 0.999 and int(diff.max()) <= 4
+
+
+# ------------------------------------------------------------------ empty and degenerate inputs
+def _scene_from_text(pkg, tmp_path, name, text):
+    rti = tmp_path / name
+    rti.write_text(text)
+    return pkg.HostScene.load(rti)
+
+
+CAM = "cam 0 0 30  -10 -10 10  10 -10 10  -10 10 10  10 10 10\n"
+
+
+def test_empty_and_lightless_scenes(pkg, gpu_renderer, oracle, reference, tmp_path):
+    """No geometry at all; geometry without any light; only an ambient light: frames, ids and ray counts equal the
+    oracle's, and the unmodified reference agrees on the frame."""
+    cases = {
+        "nothing.rti": CAM,
+        "dark.rti": CAM + "mat 0.1 0.1 0.1 0.5 0.5 0.5 0.3 0.3 0.3 10 0.5 0.5 0.5\nsph 0 0 0 4\n",
+        "ambient.rti": CAM + "lta 0.4 0.5 0.6\nmat 0.5 0.4 0.3 0.5 0.5 0.5 0.3 0.3 0.3 10 0 0 0\nsph 0 0 0 4\ntri -8 -8 -3 8 -8 -3 0 8 -3\n",
+        "lights_only.rti": CAM + "ltp 5 5 5 1 1 1\nltd 0 -1 0 1 1 1\nlta 1 1 1\n",
+    }
+    for name, text in cases.items():
+        sc = _scene_from_text(pkg, tmp_path, name, text)
+        gpu_renderer.upload(sc)
+        for (w, h, depth) in [(40, 30, 3), (1, 1, 0)]:
+            rgb = gpu_renderer.render(w, h, depth)
+            st = gpu_renderer.stats()
+            o_rgb, o_geom, o_face, counts = oracle.render(sc.flat, w, h, depth)
+            geom, face = gpu_renderer.primary_ids(w, h)
+            assert np.array_equal(geom, o_geom) and np.array_equal(face, o_face), name
+            assert [st["rays_primary"], st["rays_shadow"], st["rays_secondary"]] == counts[:3], name
+            assert np.abs(rgb - o_rgb).max() <= FP64_TOL, name
+        href = reference.load(tmp_path / name)
+        r_rgb, _, _, _ = reference.render(href, 40, 30, 3, threads=2)
+        assert np.abs(gpu_renderer.render(40, 30, 3) - r_rgb).max() <= FP64_TOL, name
+        img = gpu_renderer.render_rgb8(40, 30, 3)
+        assert np.array_equal(img, quantize(gpu_renderer.render(40, 30, 3)))
+
+
+def test_lbvh_corner_sizes(pkg, gpu_renderer, oracle, tmp_path):
+    """Meshes of one and two faces (an LBVH of a single leaf / a single node) and 65 spheres (the smallest count that
+    moves the spheres from the flat list into the LBVH)."""
+    one = tmp_path / "one.obj"
+    one.write_text("v -5 -5 0\nv 5 -5 0\nv 0 5 0\nf 1 2 3\n")
+    two = tmp_path / "two.obj"
+    two.write_text("v -5 -5 0\nv 5 -5 0\nv 0 5 0\nv 0 -9 1\nf 1 2 3\nf 1 4 2\n")
+    head = CAM + "lta 0.1 0.1 0.1\nltp 10 20 30 1 1 1\nmat 0.1 0.1 0.1 0.6 0.5 0.4 0.3 0.3 0.3 10 0.3 0.3 0.3\n"
+    spheres = "".join(f"sph {-8 + 2 * (i % 9)} {-7 + 2 * (i // 9)} {-(i % 5)} 0.8\n" for i in range(65))
+    cases = {"one.rti": head + f'obj "{one}"\n', "two.rti": head + f'obj "{two}"\n', "s65.rti": head + spheres,
+             "mix.rti": head + spheres + f'obj "{two}"\n'}
+    for name, text in cases.items():
+        sc = _scene_from_text(pkg, tmp_path, name, text)
+        gpu_renderer.upload(sc)
+        w, h, depth = 64, 48, 4
+        rgb = gpu_renderer.render(w, h, depth)
+        st = gpu_renderer.stats()
+        o_rgb, o_geom, o_face, counts = oracle.render(sc.flat, w, h, depth)
+        geom, face = gpu_renderer.primary_ids(w, h)
+        assert np.array_equal(geom, o_geom) and np.array_equal(face, o_face), name
+        assert [st["rays_primary"], st["rays_shadow"], st["rays_secondary"]] == counts[:3], name
+        assert np.abs(rgb - o_rgb).max() <= FP64_TOL, name
+        b = gpu_renderer.render(w, h, depth, flags=pkg.RT_FLAG_BRUTE_FORCE)
+        assert np.abs(rgb - b).max() <= FP64_TOL, name
+
+
+def test_more_devices_than_tiles(pkg, scenes, same_device_multi):
+    """A frame of one tile (or one pixel) rendered with n_gpus = 3: two devices own nothing and must not disturb the frame."""
+    r = pkg.Renderer(0)
+    try:
+        r.upload(scenes("input-05"))
+        for (w, h) in [(1, 1), (20, 17), (33, 31)]:
+            a = r.render(w, h, 4)
+            b = r.render(w, h, 4, n_gpus=3)
+            assert np.abs(a - b).max() <= FP64_TOL
+            assert np.array_equal(r.render_rgb8(w, h, 4), r.render_rgb8(w, h, 4, n_gpus=3))
+    finally:
+        r.close()
