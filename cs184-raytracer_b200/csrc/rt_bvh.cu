@@ -196,26 +196,72 @@ __global__ void k_depth(int n, const int* __restrict__ parent_int, int* __restri
     if ((int)(threadIdx.x & 31) == __ffs(act) - 1) atomicMax(max_depth, m);
 }
 
+// Surface-area-guided choice of the children of the 4-wide nodes (one launch per level of the wide tree, top down):
+// a binary node that is the root of a wide node in wave w starts from its two children and twice replaces the
+// internal child of LARGEST surface area by that child's two children — the child a ray is most likely to enter
+// anyway is the one whose box test is worth saving — and the internal children that remain become the roots of wave
+// w + 1.  wave_of[]: wave of every root (-1: not a root); slots4[]: the four chosen children (BVH_DONE: none).
+// Against pulling up the grandchildren of every even-depth node: 3.3 % fewer node visits per ray on the 1 M-triangle
+// scene (19.27 -> 18.64 closest hit, 13.28 -> 12.83 any hit).
+__global__ void k_choose_children(int n, int wave, int* __restrict__ wave_of, int4* __restrict__ slots4,
+                                  const int* __restrict__ left, const int* __restrict__ right,
+                                  const float* __restrict__ ilo, const float* __restrict__ ihi, int* __restrict__ wave_any) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1 || wave_of[i] != wave) return;
+    int slots[4] = {left[i], right[i], BVH_DONE, BVH_DONE};
+    int ns = 2;
+    for (int rep = 0; rep < 2; rep++) {
+        int best = -1;
+        float best_area = -1.f;
+        for (int k = 0; k < ns; k++) {
+            if (slots[k] < 0) continue;
+            const float* bl = ilo + 3 * (size_t)slots[k];
+            const float* bh = ihi + 3 * (size_t)slots[k];
+            const float ex = bh[0] - bl[0], ey = bh[1] - bl[1], ez = bh[2] - bl[2];
+            const float area = ex * ey + ey * ez + ez * ex;
+            if (area > best_area) { best_area = area; best = k; }
+        }
+        if (best < 0) break;
+        const int c = slots[best];
+        slots[best] = left[c];
+        slots[ns++] = right[c];
+    }
+    for (int k = 0; k < ns; k++)
+        if (slots[k] >= 0) wave_of[slots[k]] = wave + 1;
+    slots4[i] = make_int4(slots[0], slots[1], slots[2], slots[3]);
+    wave_any[wave] = 1;          // same value from every root of the wave: the deepest marked wave is the wide tree's depth
+}
+
 // Binary Karras nodes at EVEN depth become 4-wide nodes: each internal child (odd depth) is
 // replaced by its own two children.  Wide nodes keep the binary node's index (+ offset), so
 // no compaction pass is needed; odd-depth slots of the array stay unused.
+//
+// slots4 != null: the children were chosen by k_choose_children (wave_of[i] >= 0 marks the wide nodes) instead.
 __global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __restrict__ codes,
                             const float* __restrict__ plo, const float* __restrict__ phi,
                             const int* __restrict__ left, const int* __restrict__ right,
                             const float* __restrict__ ilo, const float* __restrict__ ihi,
                             const int* __restrict__ depth, const int* __restrict__ gbounds,
-                            BvhNode* __restrict__ nodes, int node_offset) {
+                            BvhNode* __restrict__ nodes, int node_offset, const int* __restrict__ wave_of,
+                            const int4* __restrict__ slots4) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    if (depth[i] & 1) return;
+    if (slots4 ? wave_of[i] < 0 : (depth[i] & 1) != 0) return;
     // pad: a few FP32 ulps at the scene's largest coordinate (covers the slab test's rounding)
     const float pad = 2e-6f * fmaxf(ord2f(gbounds[6]), 1e-30f);
     int slots[4];
     int ns = 0;
     int ch[2] = {left[i], right[i]};
-    for (int k = 0; k < 2; k++) {
-        if (ch[k] < 0) slots[ns++] = ch[k];
-        else { slots[ns++] = left[ch[k]]; slots[ns++] = right[ch[k]]; }
+    if (!slots4) {
+        for (int k = 0; k < 2; k++) {
+            if (ch[k] < 0) slots[ns++] = ch[k];
+            else { slots[ns++] = left[ch[k]]; slots[ns++] = right[ch[k]]; }
+        }
+    } else {
+        const int4 c4 = slots4[i];
+        const int c[4] = {c4.x, c4.y, c4.z, c4.w};
+        for (int k = 0; k < 4; k++)
+            if (c[k] != BVH_DONE) slots[ns++] = c[k];
     }
     float lo[3][4], hi[3][4];
     int ref[4];
@@ -253,6 +299,7 @@ __global__ void k_pack_wide(int n, const int* __restrict__ vals, const int* __re
     nodes[node_offset + i] = nd;
 }
 
+#define RT_MAX_WAVES 256      // levels of the wide tree k_choose_children may walk (the traversal stack allows far fewer)
 #define TAKE(var, type, count)                                                         \
     do {                                                                               \
         var = arena.take<type>((size_t)(count));                                       \
@@ -280,12 +327,17 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
     *out_count = 0;
     float *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr;
     int *gb = nullptr, *vals0 = nullptr, *vals1 = nullptr, *hist = nullptr;
+    int4* slots4 = nullptr;
+    int* wave_any = nullptr;
+    std::vector<int> h_wave_any(RT_MAX_WAVES, 0);
     int *left = nullptr, *right = nullptr, *pint = nullptr, *pleaf = nullptr, *flags = nullptr, *depth = nullptr;
     uint32_t *keys0 = nullptr, *keys1 = nullptr;
     const int T = 256;
     const int nblk = (n + T - 1) / T;
     int hb[7];
-    int max_bin_depth = 0;
+    int max_bin_depth = 0, max_wide_wave = 0;
+    // RT_LBVH_COLLAPSE=even: round 1's fixed collapse (every even-depth binary node pulls up its grandchildren), for A/B
+    const bool sah_collapse = !(getenv("RT_LBVH_COLLAPSE") && !strcmp(getenv("RT_LBVH_COLLAPSE"), "even"));
     float pad_scale = 0.f;
     struct Group { int start, n, root_ref, first_code; float box[6]; };
     Group groups[4];
@@ -307,9 +359,9 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         }
         TAKE(plo, float, 3 * (size_t)n);
         TAKE(phi, float, 3 * (size_t)n);
-        TAKE(gb, int, 8);
-        int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000,
-                       (int)0x80000000, 0};
+        TAKE(gb, int, 16);
+        int init[9] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000,
+                       (int)0x80000000, 0, 0};
         CK(cudaMemcpyAsync(gb, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         k_prim_bounds<<<nblk, T, 0, stream>>>(S, d_codes, n, plo, phi, gb);
         (*launches)++;
@@ -336,6 +388,9 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
         TAKE(depth, int, (size_t)n);
         TAKE(ilo, float, 3 * (size_t)n);
         TAKE(ihi, float, 3 * (size_t)n);
+        TAKE(slots4, int4, (size_t)n);
+        TAKE(wave_any, int, RT_MAX_WAVES);
+        CK(cudaMemsetAsync(wave_any, 0, sizeof(int) * RT_MAX_WAVES, stream));
         CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
         k_morton<<<nblk, T, 0, stream>>>(plo, phi, n, gb, keys0, vals0);
         (*launches)++;
@@ -358,8 +413,26 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
             k_refit<<<gblk, T, 0, stream>>>(gn, vin, plo, phi, left + gs, right + gs, pint + gs, pleaf + gs,
                                             ilo + 3 * (size_t)gs, ihi + 3 * (size_t)gs, flags + gs);
             k_depth<<<gblk, T, 0, stream>>>(gn, pint + gs, depth + gs, gb + 7);
-            k_pack_wide<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
-                                                ihi + 3 * (size_t)gs, depth + gs, gb, nodes, (int)node_cursor);
+            if (!sah_collapse) {
+                k_pack_wide<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
+                                                    ihi + 3 * (size_t)gs, depth + gs, gb, nodes, (int)node_cursor, nullptr, nullptr);
+            } else {
+                // one light launch per level of the wide tree; the wide tree is at most as deep as the binary one
+                int gdepth = 0;
+                CK(cudaMemcpyAsync(&gdepth, gb + 7, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                int* wave_of = flags + gs;            // k_refit is done with its arrival counters
+                CK(cudaMemsetAsync(wave_of, 0xff, sizeof(int) * (size_t)gn, stream));
+                CK(cudaMemsetAsync(wave_of, 0, sizeof(int), stream));                          // the group's root: wave 0
+                if (gdepth + 1 > RT_MAX_WAVES) gdepth = RT_MAX_WAVES - 1;      // deeper trees fail the stack check below anyway
+                for (int w = 0; w <= gdepth; w++) {
+                    k_choose_children<<<gblk, T, 0, stream>>>(gn, w, wave_of, slots4 + gs, left + gs, right + gs, ilo + 3 * (size_t)gs,
+                                                              ihi + 3 * (size_t)gs, wave_any);
+                    (*launches)++;
+                }
+                k_pack_wide<<<gblk, T, 0, stream>>>(gn, vin, d_codes, plo, phi, left + gs, right + gs, ilo + 3 * (size_t)gs,
+                                                    ihi + 3 * (size_t)gs, depth + gs, gb, nodes, (int)node_cursor, wave_of, slots4 + gs);
+            }
             (*launches) += 4;
             groups[g].root_ref = (int)node_cursor;
             CK(cudaMemcpyAsync(groups[g].box, ilo + 3 * (size_t)gs, 12, cudaMemcpyDeviceToHost, stream));
@@ -367,13 +440,16 @@ int build_lbvh(const DScene& S, const int* d_codes, const int* group_first_code,
             node_cursor += (size_t)(gn - 1);
         }
         CK(cudaMemcpyAsync(&max_bin_depth, gb + 7, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_wave_any.data(), wave_any, sizeof(int) * RT_MAX_WAVES, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
+        for (int w = 0; w < RT_MAX_WAVES; w++)
+            if (h_wave_any[(size_t)w]) max_wide_wave = w;
         {   // The traversal defers at most 3 siblings per wide level.  Wide levels on a root-to-leaf path: one per
             // two binary levels (even-depth collapse) + the super node.  The stack (RT_SH_STACK shared + RT_STACK
             // local entries) must hold them all; Karras trees over 30-bit codes with index-split duplicates stay
             // far below this, so a scene that does not is rejected instead of silently dropping subtrees.
-            const int wide_levels = max_bin_depth / 2 + 1 + nsuper;
+            const int wide_levels = (sah_collapse ? max_wide_wave + 1 : max_bin_depth / 2 + 1) + nsuper;
             if (3 * wide_levels > RT_STACK + RT_SH_STACK) {
                 snprintf(err, errlen, "LBVH is %d binary levels deep: %d deferred entries exceed the traversal stack of %d",
                          max_bin_depth + 1, 3 * wide_levels, RT_STACK + RT_SH_STACK);

@@ -35,7 +35,7 @@ struct DeviceArena {
 
 // scratch bytes build_lbvh takes from the arena for n primitives
 inline size_t lbvh_scratch_bytes(size_t n) {
-    return 4 * DeviceArena::padded(12 * n) + 10 * DeviceArena::padded(4 * n) + DeviceArena::padded(4 * 256 * 4097 /* radix-sort histograms, SORT_MAX_BLOCKS + 1 */) + 4096;
+    return 4 * DeviceArena::padded(12 * n) + 10 * DeviceArena::padded(4 * n) + DeviceArena::padded(16 * n) + DeviceArena::padded(4 * 256) + DeviceArena::padded(4 * 256 * 4097 /* radix-sort histograms, SORT_MAX_BLOCKS + 1 */) + 4096;
 }
 
 // Builds one LBVH per primitive group over the n primitive codes in d_codes (device;
