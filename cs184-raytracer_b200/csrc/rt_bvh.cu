@@ -1,6 +1,6 @@
 // rt_bvh.cu — GPU LBVH build: primitive bounds -> 30-bit Morton codes -> hand-written
 // LSD radix sort (no CUB) -> Karras hierarchy (pure integer, deterministic) -> bottom-up
-// refit -> 64-byte node pairs.  It replaces the reference's only acceleration structure,
+// refit -> surface-area-guided collapse into 128-byte 4-wide nodes.  It replaces the reference's only acceleration structure,
 // one object-space AABB per .obj mesh (Mesh::updateBoundingBox src/geometry.cpp:145-162,
 // hitsBoundingBox src/geometry.cpp:5-29).  The boxes only CULL (FP32, padded outward);
 // every hit decision is still the exact FP64 test in rt_device.cuh.
