@@ -510,3 +510,36 @@ def test_more_devices_than_tiles(pkg, scenes, same_device_multi):
             assert np.array_equal(r.render_rgb8(w, h, 4), r.render_rgb8(w, h, 4, n_gpus=3))
     finally:
         r.close()
+
+
+# ------------------------------------------------------------------ every scene the reference ships
+ALL_LOADABLE = sorted(p for p in list((GOLDEN / "inputs").glob("*.rti")) + list((GOLDEN / "excess_inputs").glob("*.rti"))
+                      if p.name not in ("teapot.rti",))   # excess teapot.rti has no teapot.obj beside it
+
+
+@pytest.mark.parametrize("path", ALL_LOADABLE, ids=lambda p: p.parent.name + "/" + p.name)
+def test_every_shipped_scene_matches_the_oracle(pkg, gpu_renderer, oracle, path):
+    """All 25 loadable scenes of the reference tree (the oracle is pinned to the live reference on each of them in
+    tests/test_oracle_vs_reference.py): hit ids, ray counts per class, FP64 frame, and per-ray castRay results."""
+    sc = pkg.HostScene.load(path)
+    gpu_renderer.upload(sc)
+    w, h, depth = 72, 54, 6
+    rgb = gpu_renderer.render(w, h, depth)
+    st = gpu_renderer.stats()
+    geom, face = gpu_renderer.primary_ids(w, h)
+    o_rgb, o_geom, o_face, counts = oracle.render(sc.flat, w, h, depth)
+    assert np.array_equal(geom, o_geom) and np.array_equal(face, o_face)
+    assert [st["rays_primary"], st["rays_shadow"], st["rays_secondary"]] == counts[:3]
+    assert st["degenerate_rays"] == counts[3]
+    assert np.abs(rgb - o_rgb).max() <= FP64_TOL
+    rng = np.random.default_rng(11)
+    n = 4000
+    org, direction = oracle.camera_rays(sc.flat, 100, 100, rng.integers(0, 10000, n))
+    g0, f0, d0, p0, n0 = oracle.cast_rays(sc.flat, org, direction)
+    org2 = np.where((g0 >= 0)[:, None], p0, org)
+    dir2 = rng.normal(size=(n, 3))
+    rev = rng.integers(0, 2, n).astype(np.uint8)
+    og = oracle.cast_rays(sc.flat, org2, dir2, rev)
+    gg = gpu_renderer.cast_rays(org2, dir2, rev)
+    for a, b in zip(gg, og):
+        assert np.array_equal(a, b)

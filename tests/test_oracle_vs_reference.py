@@ -149,3 +149,28 @@ def test_big_fixture_consistency(pkg, oracle):
     assert np.array_equal(g, fx["geom"][::s, ::s][::6, ::6].ravel().astype(np.int32))
     assert np.array_equal(f, fx["face"][::s, ::s][::6, ::6].ravel())
     assert np.array_equal(quantize(fx["rgb_sub"]), fx["rgb8"][::s, ::s])
+
+
+ALL_LOADABLE = sorted(p for p in list((GOLDEN / "inputs").glob("*.rti")) + list((GOLDEN / "excess_inputs").glob("*.rti"))
+                      if p.name not in ("teapot.rti",))   # excess teapot.rti has no teapot.obj beside it
+
+
+@pytest.mark.parametrize("path", ALL_LOADABLE, ids=lambda p: p.parent.name + "/" + p.name)
+def test_oracle_equals_live_reference_on_every_shipped_scene(pkg, oracle, reference, path):
+    """Every loadable scene the reference ships (25), not only the 15 with stored fixtures: a 40x30 frame of the
+    restatement against the live unmodified reference — FP64 frame, geometry ids and castRay count bit for bit."""
+    sc = pkg.HostScene.load(path)
+    h = reference.load(path)
+    w, hh, depth = 40, 30, 6
+    rgb, geom, _, counts = oracle.render(sc.flat, w, hh, depth)
+    counting = getattr(test_oracle_equals_live_reference_on_every_shipped_scene, "_counting", None)
+    if counting is None:
+        from conftest import Reference
+        counting = Reference(counting=True)
+        test_oracle_equals_live_reference_on_every_shipped_scene._counting = counting
+    r_rgb, r_geom, _, calls = counting.render(counting.load(path), w, hh, depth, threads=4, ids=True)
+    assert np.array_equal(rgb, r_rgb)
+    assert np.array_equal(geom, r_geom)
+    assert sum(counts[:3]) == calls and counts[3] == 0
+    a_rgb, _, _, _ = reference.render(h, w, hh, depth, threads=4)
+    assert np.array_equal(a_rgb, r_rgb)
